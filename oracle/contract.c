@@ -1,0 +1,295 @@
+/* TEST INFRASTRUCTURE ONLY -- op-for-op fp64 arithmetic contract of PyPOLAR's per-pixel analysis path.
+ *
+ * Plain scalar C restatement of what the reference's NumPy/SciPy statements compute, one separately
+ * rounded IEEE-754 double operation at a time, in the reference's evaluation order.
+ * It exists to pin, on a CPU, the exact sequence the CUDA kernels replay. It is checked bit-for-bit
+ * against oracle/restate.py (which calls the same NumPy/SciPy routines as the reference) and against the
+ * golden vectors generated from the unmodified reference (tests/golden). It is never linked into or
+ * called by the product.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC  (contraction MUST stay off; the one
+ * fused operation of the path is spelled fma()).
+ *
+ * PP = pypolar/PyPOLAR.py, PC = pypolar/pypolar_classes.py (cchandre/Polarimetry v2.9.4).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+enum { PC_U8 = 0, PC_U16 = 1, PC_F32 = 2, PC_F64 = 3 };
+enum { M_1PF = 0, M_CARS = 1, M_SRS = 2, M_SHG = 3, M_2PF = 4, M_4POLAR2D = 5, M_4POLAR3D = 6 };
+
+static double load_val(const void *v, int dtype, long k) {
+    switch (dtype) {
+    case PC_U8: return (double)((const uint8_t *)v)[k];
+    case PC_U16: return (double)((const uint16_t *)v)[k];
+    case PC_F32: return (double)((const float *)v)[k];
+    default: return ((const double *)v)[k];
+    }
+}
+
+/* numpy maximum(x, 0): NaN propagates */
+static double max0(double x) { return (x != x) ? x : (x > 0.0 ? x : 0.0); }
+
+/* scipy.ndimage 'reflect' (half-sample symmetric) index: d c b a | a b c d | d c b a */
+static long reflect_idx(long k, long L) {
+    while (k < 0 || k >= L) {
+        if (k < 0) k = -k - 1;
+        if (k >= L) k = 2 * L - 1 - k;
+    }
+    return k;
+}
+
+/* scipy.ndimage.uniform_filter1d, mode='reflect', origin 0, on one strided line (in place allowed
+ * through the extension buffer `ext`, L + n doubles). Running sum: tmp += new - old; out = tmp / n.
+ * Restates the 1-D passes behind PP:2945 and PC:264. */
+static void box_line(double *line, long stride, long L, int n, double *ext) {
+    long h = n / 2, E = L + n - 1;
+    for (long k = 0; k < E; ++k) ext[k] = line[reflect_idx(k - h, L) * stride];
+    double tmp = 0.0;
+    for (int k = 0; k < n; ++k) tmp = tmp + ext[k];
+    line[0] = tmp / (double)n;
+    for (long k = 1; k < L; ++k) {
+        tmp = tmp + (ext[k + n - 1] - ext[k - 1]);
+        line[k * stride] = tmp / (double)n;
+    }
+}
+
+/* uniform_filter(f, size=[0,bh,bw]) on [P,H,W]: axis 1 (H) first, then axis 2 (W); sizes <= 1 skipped. */
+void pc_box(double *f, long P, long H, long W, int bh, int bw) {
+    long m = (H > W ? H : W) + (bh > bw ? bh : bw) + 2;
+    double *ext = (double *)malloc(sizeof(double) * m);
+    for (long p = 0; p < P; ++p) {
+        double *pl = f + p * H * W;
+        if (bh > 1)
+            for (long x = 0; x < W; ++x) box_line(pl + x, W, H, bh, ext);
+        if (bw > 1)
+            for (long y = 0; y < H; ++y) box_line(pl + y * W, 1, W, bw, ext);
+    }
+    free(ext);
+}
+
+/* field = max(values - sub, 0) ; CARS: sqrt ; 4POLAR: planes 1 <-> 2. Restates PP:2953-2957. */
+void pc_field(const void *v, int dtype, long N, long H, long W, double sub, int do_sqrt, int swap12, double *out) {
+    long P = H * W;
+    for (long i = 0; i < N; ++i) {
+        long src = i;
+        if (swap12 && (i == 1 || i == 2)) src = 3 - i;
+        for (long p = 0; p < P; ++p) {
+            double x = max0(load_val(v, dtype, src * P + p) - sub);
+            out[i * P + p] = do_sqrt ? sqrt(x) : x;
+        }
+    }
+}
+
+/* Total-intensity image: sum_i max(v_i - dark, 0), then 2-D box filter. Restates PC:260-264. */
+void pc_intensity(const void *v, int dtype, long N, long H, long W, double dark, int bh, int bw, double *out) {
+    long P = H * W;
+    for (long p = 0; p < P; ++p) {
+        double s = max0(load_val(v, dtype, p) - dark);
+        for (long i = 1; i < N; ++i) s = s + max0(load_val(v, dtype, i * P + p) - dark);
+        out[p] = s;
+    }
+    if (!(bh == 1 && bw == 1)) pc_box(out, 1, H, W, bh, bw);
+}
+
+static int finite_d(double x) { return x == x && x - x == 0.0; }
+
+/* np.mod(a, b), b > 0 (python-sign modulo). */
+static double pymod(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0) {
+        if (r < 0.0) r = r + b;
+    } else {
+        r = copysign(0.0, b);
+    }
+    return r;
+}
+
+/* Harmonic block PP:2987-3000. nharm = 1 (1PF) or 2 (CARS/SRS/SHG/2PF).
+ * Outputs: a0 (NaN where 0), normalised A2,B2,(A4,B4), chi2, mask (in/out, uint8). fit (optional, may be
+ * NULL) receives field_fit [N,H,W]. */
+void pc_harmonics(const double *f, long N, long H, long W, int nharm, const double *c2, const double *s2,
+                  const double *c4, const double *s4, double chi2thr, uint8_t *mask, double *a0o, double *A2,
+                  double *B2, double *A4, double *B4, double *chi2o, double *fit_out) {
+    long P = H * W;
+    double k2 = 2.0 / (double)N;
+    double *fit = (double *)malloc(sizeof(double) * N);
+    for (long p = 0; p < P; ++p) {
+        double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0;
+        for (long i = 0; i < N; ++i) {
+            double x = f[i * P + p];
+            S0 = S0 + x;
+            Sc = Sc + x * c2[i];
+            Ss = Ss + x * s2[i];
+            if (nharm == 2) {
+                Sc4 = Sc4 + x * c4[i];
+                Ss4 = Ss4 + x * s4[i];
+            }
+        }
+        double a0 = S0 / (double)N;
+        if (a0 == 0.0) a0 = NAN;
+        double a2r = k2 * Sc, a2i = k2 * Ss, a4r = k2 * Sc4, a4i = k2 * Ss4;
+        int valid = 1;
+        double acc = 0.0;
+        for (long i = 0; i < N; ++i) {
+            /* numpy's SIMD complex multiply: Re(a2 * conj(e2)) = fma(a2r, c, -(a2i * (-s))) */
+            double ft = a0 + fma(a2r, c2[i], -(a2i * (-s2[i])));
+            if (nharm == 2) ft = ft + fma(a4r, c4[i], -(a4i * (-s4[i])));
+            fit[i] = ft;
+            if (!(ft > 0.0 && finite_d(ft))) valid = 0;
+            double d = f[i * P + p] - ft;
+            acc = acc + (d * d) / ft;
+            if (fit_out) fit_out[i * P + p] = ft;
+        }
+        double chi2 = acc / (double)N;
+        double inv = 1.0 / a0;
+        double x;
+        x = a2r * inv; A2[p] = finite_d(x) ? x : NAN;
+        x = a2i * inv; B2[p] = finite_d(x) ? x : NAN;
+        /* divide_ext NaNs the whole complex number if either part is non-finite (PC:61) */
+        if (!(finite_d(A2[p]) && finite_d(B2[p]))) A2[p] = B2[p] = NAN;
+        if (nharm == 2) {
+            x = a4r * inv; A4[p] = x;
+            x = a4i * inv; B4[p] = x;
+            if (!(finite_d(A4[p]) && finite_d(B4[p]))) A4[p] = B4[p] = NAN;
+        }
+        a0o[p] = a0;
+        chi2o[p] = chi2;
+        mask[p] = (uint8_t)(mask[p] && valid && (chi2 <= chi2thr) && (chi2 > 0.0));
+    }
+    free(fit);
+}
+
+/* scipy RegularGridInterpolator cell search: g[i] <= x < g[i+1], last cell closed. */
+static long find_cell(const double *g, long n, double x) {
+    if (x == g[n - 1]) return n - 2;
+    long lo = 0, hi = n - 1; /* invariant g[lo] <= x < g[hi] */
+    while (hi - lo > 1) {
+        long mid = (lo + hi) / 2;
+        if (x >= g[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+static double bilinear(const double *T, long n, long i0, long i1, double t0, double t1) {
+    double u0 = 1.0 - t0, u1 = 1.0 - t1;
+    double w00 = (1.0 * u0) * u1, w01 = (1.0 * u0) * t1, w10 = (1.0 * t0) * u1, w11 = (1.0 * t0) * t1;
+    double v = 0.0;
+    v = v + T[i0 * n + i1] * w00;
+    v = v + T[i0 * n + i1 + 1] * w01;
+    v = v + T[(i0 + 1) * n + i1] * w10;
+    v = v + T[(i0 + 1) * n + i1 + 1] * w11;
+    return v;
+}
+
+/* 1PF inversion through the disk-cone table. Restates PP:3017-3026 (+ interpn semantics). */
+void pc_lut_1pf(const double *A2, const double *B2, long P, const double *rho_t, const double *psi_t,
+                const double *g, long n, double rotation, uint8_t *mask, double *rho, double *psi) {
+    for (long p = 0; p < P; ++p) {
+        rho[p] = NAN; psi[p] = NAN;
+        if (!mask[p]) continue;
+        double x = A2[p], y = B2[p], r = NAN, q = NAN;
+        if (x == x && y == y && !(x < g[0]) && !(x > g[n - 1]) && !(y < g[0]) && !(y > g[n - 1])) {
+            long i0 = find_cell(g, n, x), i1 = find_cell(g, n, y);
+            double t0 = (x - g[i0]) / (g[i0 + 1] - g[i0]);
+            double t1 = (y - g[i1]) / (g[i1 + 1] - g[i1]);
+            r = bilinear(rho_t, n, i0, i1, t0, t1);
+            q = bilinear(psi_t, n, i0, i1, t0, t1);
+        }
+        if (finite_d(r)) r = pymod(r + rotation, 180.0);
+        rho[p] = r; psi[p] = q;
+        mask[p] = (uint8_t)(finite_d(r) && finite_d(q));
+    }
+}
+
+static const double RAD2DEG = 180.0 / 3.141592653589793238462643383279502884;
+static const double DEG2RAD = 3.141592653589793238462643383279502884 / 180.0;
+
+/* 4-harmonic outputs. Restates PP:3027-3040. sshg may be NULL. */
+void pc_out_4harm(const double *A2, const double *B2, const double *A4, const double *B4, long P, double rotation,
+                  const uint8_t *mask, double *rho, double *s2, double *s4, double *sshg) {
+    for (long p = 0; p < P; ++p) {
+        rho[p] = NAN; s2[p] = NAN; s4[p] = NAN;
+        if (sshg) sshg[p] = NAN;
+        if (!mask[p]) continue;
+        double r = (atan2(B2[p], A2[p]) * RAD2DEG) / 2.0;
+        r = pymod(r + rotation, 180.0);
+        double ab2 = hypot(A2[p], B2[p]), ab4 = hypot(A4[p], B4[p]);
+        rho[p] = r;
+        s2[p] = 1.5 * ab2;
+        s4[p] = (6.0 * ab4) * cos(4.0 * (0.25 * atan2(B4[p], A4[p]) - r * DEG2RAD));
+        if (sshg) sshg[p] = (-0.5 * (ab4 - ab2)) / (ab4 + ab2) - 0.65;
+    }
+}
+
+/* 4POLAR 2D/3D. f has 4 planes already swapped to (0,90,45,135). Restates PP:3001-3014, PP:3041-3051.
+ * invK is [rows,4] row-major, rows = 3 (2D) or 4 (3D). eta may be NULL (2D). */
+void pc_4polar(const double *f, long P, const double *invK, int three_d, double rotation, uint8_t *mask,
+               double *a0o, double *rho, double *psi, double *eta) {
+    int rows = three_d ? 4 : 3;
+    for (long p = 0; p < P; ++p) {
+        double m[4] = {0, 0, 0, 0};
+        for (int r = 0; r < rows; ++r) {
+            double acc = 0.0;
+            for (int j = 0; j < 4; ++j) acc = acc + invK[r * 4 + j] * f[j * P + p];
+            m[r] = acc;
+        }
+        double s = three_d ? ((m[0] + m[1]) + m[2]) : ((m[0] + m[1]) + 0.0);
+        if (s == 0.0) s = NAN;
+        double pxy = (m[0] - m[1]) / s;
+        double puv = (2.0 * m[three_d ? 3 : 2]) / s;
+        double pzz = 0.0, lam;
+        if (three_d) {
+            pzz = m[2] / s;
+            lam = (1.0 - (pzz + sqrt(puv * puv + pxy * pxy))) / 2.0;
+        } else {
+            double p2 = sqrt(puv * puv + pxy * pxy);
+            lam = (1.0 - p2) / (3.0 - p2);
+        }
+        double a0 = ((((f[p] + f[P + p]) + f[2 * P + p]) + f[3 * P + p]) / 4.0) / 4.0;
+        if (a0 == 0.0) a0 = NAN;
+        int ok = mask[p] && (lam < 1.0 / 3.0) && (lam > 0.0) && (three_d ? (pzz > lam) : 1);
+        mask[p] = (uint8_t)ok;
+        rho[p] = NAN; psi[p] = NAN;
+        if (eta) eta[p] = NAN;
+        a0o[p] = a0;
+        if (!ok) continue;
+        rho[p] = pymod(0.5 * (atan2(puv, pxy) * RAD2DEG) + rotation, 180.0);
+        psi[p] = 2.0 * (acos((-1.0 + sqrt(9.0 - 24.0 * lam)) / 2.0) * RAD2DEG);
+        if (eta) eta[p] = acos(sqrt((pzz - lam) / (1.0 - 3.0 * lam))) * RAD2DEG;
+    }
+}
+
+/* intmap = a0 where mask else NaN (PP:3052); Rho_angle (PP:3069-3072); Rho_contour (PP:3059-3068). */
+void pc_tail(long P, const uint8_t *mask, double *a0, const double *rho, double reference_angle, double *rho_angle,
+             const double *edge, double *rho_contour) {
+    for (long p = 0; p < P; ++p) {
+        if (!mask[p]) a0[p] = NAN;
+        if (rho_angle) rho_angle[p] = (rho[p] == rho[p]) ? pymod(rho[p] - reference_angle, 180.0) : NAN;
+        if (rho_contour) rho_contour[p] = (finite_d(rho[p]) && finite_d(edge[p])) ? pymod(rho[p] - edge[p], 180.0) : NAN;
+    }
+}
+
+/* Variable.histo numerics, PC:340-369 + np.histogram with explicit edges:
+ * sel & finite(X); Rho/Rho_angle: d = mod(2(d+rot),360)/2; polar3: d>=90 -> 180-d;
+ * bins [e_k, e_{k+1}), last closed; outside dropped. */
+void pc_hist(const double *X, const uint8_t *sel, long P, int is_rho, double rotation_fig, int fold90,
+             const double *edges, int nbins, int64_t *counts) {
+    for (int k = 0; k < nbins; ++k) counts[k] = 0;
+    for (long p = 0; p < P; ++p) {
+        double d = X[p];
+        if ((sel && !sel[p]) || !finite_d(d)) continue;
+        if (is_rho) d = pymod(2.0 * (d + rotation_fig), 360.0) / 2.0;
+        if (fold90 && d >= 90.0) d = 180.0 - d;
+        if (d < edges[0] || d > edges[nbins]) continue;
+        int lo = 0, hi = nbins; /* edges[lo] <= d, find largest lo with edges[lo] <= d */
+        if (d == edges[nbins]) { counts[nbins - 1]++; continue; }
+        while (hi - lo > 1) {
+            int mid = (lo + hi) / 2;
+            if (d >= edges[mid]) lo = mid; else hi = mid;
+        }
+        counts[lo]++;
+    }
+}
