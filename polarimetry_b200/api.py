@@ -1,0 +1,614 @@
+"""Host-side API of polarimetry_b200: the PyPOLAR analysis path on a B200, behind the reference's own names.
+
+Two layers:
+  * `Engine` -- one per GPU; owns a `pb_ctx` of libpolarb200.so. `Engine.analyze()` is the fused entry
+    (raw stack in -> rho/psi/S2/S4/eta maps, intensity map, mask, histograms out), the equivalent of
+    `Polarimetry.analyze_stack` (PyPOLAR.py:2948-2979) without the GUI. `analyze_batch` / `analyze_host`
+    are the many-stack and host-buffer forms.
+  * drop-in functions with the reference's signatures -- `compute_fields` (PP:2981), `binning` (PP:2942),
+    `get_intensity` (PC:260), `histo` (PC:339-369 numerics) -- and `install()` which rebinds them on an
+    imported reference module.
+PyTorch is used for device memory and streams only; all arithmetic is in the CUDA library. There is no
+CPU fallback: every entry point raises if the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field as _field
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import PbOutputs, PbParams
+
+METHODS = ('1PF', 'CARS', 'SRS', 'SHG', '2PF', '4POLAR 2D', '4POLAR 3D')
+VAR_NAMES = {'1PF': ['Rho', 'Psi'], 'CARS': ['Rho', 'S2', 'S4'], 'SRS': ['Rho', 'S2', 'S4'], '2PF': ['Rho', 'S2', 'S4'],
+             'SHG': ['Rho', 'S2', 'S4', 'S_SHG'], '4POLAR 2D': ['Rho', 'Psi'], '4POLAR 3D': ['Rho', 'Psi', 'Eta']}
+# default display ranges of the reference GUI (PyPOLAR.py:1719-1730)
+DEFAULT_RANGES = {'Rho': (0.0, 180.0), 'Rho_contour': (0.0, 180.0), 'Rho_angle': (0.0, 180.0), 'Psi': (40.0, 180.0),
+                  'S2': (0.0, 1.0), 'S4': (-1.0, 1.0), 'S_SHG': (-1.0, 1.0), 'Eta': (0.0, 90.0)}
+
+
+@dataclass
+class AnalysisParams:
+    """The settings `analyze_stack` reads from the GUI (PP:2950-2968); defaults as in `startup` (PP:626-639)."""
+    method: str = '1PF'
+    dark: float = 0.0
+    removed_intensity: float = 0.0
+    bins: Tuple[int, int] = (1, 1)          # (size along H, size along W) = (bin_spinboxes[0], [1]), PP:2943-2945
+    polar_dir: str = 'clockwise'
+    offset_angle: float = 0.0
+    rotation: Tuple[float, float, float] = (0.0, 0.0, 0.0)    # stick, figure, reference (PP:552)
+    chi2threshold: float = 500.0
+    ilow: float = 0.0
+    nbins: int = 60
+    ranges: Dict[str, Tuple[float, float]] = _field(default_factory=lambda: dict(DEFAULT_RANGES))
+    out_dtype: str = 'float64'              # 'float64' (bit-comparable maps) or 'float32' (throughput mode)
+    exact_chi2: bool = False                # disable the certified chi2 screening
+    force_unfused: bool = False             # run the separate kernels instead of the fused one
+
+
+class Calibration:
+    """Disk-cone table (1PF) or inverse polarization matrix (4POLAR): the data side of the reference's
+    `Calibration` (PC:411-464). The tables themselves are the user's / the reference's data files."""
+
+    def __init__(self, rho_table=None, psi_table=None, n: Optional[int] = None, invK=None, name: str = ''):
+        self.name = name
+        self.rho_table = None if rho_table is None else np.ascontiguousarray(rho_table, dtype=np.float64)
+        self.psi_table = None if psi_table is None else np.ascontiguousarray(psi_table, dtype=np.float64)
+        if self.rho_table is not None:
+            n = int(n if n is not None else self.rho_table.shape[0])
+            self.grid = np.linspace(-1, 1, n, dtype=np.float64)           # PC:463
+        self.invKmat = None if invK is None else np.ascontiguousarray(invK, dtype=np.float64)
+
+    @classmethod
+    def from_mat(cls, path) -> 'Calibration':
+        """Disk-cone `.mat` with RoTest / PsiTest / NbMapValues (PC:460-464)."""
+        from scipy.io import loadmat
+        d = loadmat(str(path), variable_names=['RoTest', 'PsiTest', 'NbMapValues'], squeeze_me=True)
+        return cls(d['RoTest'], d['PsiTest'], int(d['NbMapValues']), name=Path(path).stem)
+
+    @classmethod
+    def from_npz(cls, path) -> 'Calibration':
+        d = np.load(str(path))
+        return cls(d['RoTest'], d['PsiTest'], int(d['NbMapValues']), name=Path(path).stem)
+
+    @classmethod
+    def from_K(cls, K, name: str = '') -> 'Calibration':
+        """4POLAR: invKmat = pinv(K) (PC:450); K is 4x3 (2D) or 4x4 (3D)."""
+        return cls(invK=np.linalg.pinv(np.asarray(K, dtype=np.float64)), name=name)
+
+    @classmethod
+    def from_K_txt(cls, path) -> 'Calibration':
+        return cls.from_K(np.genfromtxt(str(path), dtype=np.float64), name=Path(path).stem)
+
+
+class Variable:
+    """Result container with the reference's field names (PC:307-327): `.name`, `.values` [H,W]."""
+
+    def __init__(self, name: str, values):
+        self.name, self.values = name, values
+
+
+@dataclass
+class Result:
+    vars: List[Variable]
+    intmap: Optional[torch.Tensor]
+    mask: Optional[torch.Tensor]
+    intensity: Optional[torch.Tensor]
+    hist: Dict[Tuple[str, Optional[int]], np.ndarray]
+    roi_map: Optional[np.ndarray] = None
+    plan: str = ''
+
+    def get_var(self, name):
+        return next((v for v in self.vars if v.name == name), None)
+
+    @property
+    def xmap(self):
+        """Column index where the pixel is valid, NaN elsewhere (PP:3056-3058), built lazily."""
+        H, W = self.mask.shape[-2:]
+        xx = torch.arange(W, device=self.mask.device, dtype=torch.float64).expand(H, W)
+        return torch.where(self.mask.bool(), xx, torch.full_like(xx, float('nan')))
+
+    @property
+    def ymap(self):
+        H, W = self.mask.shape[-2:]
+        yy = torch.arange(H, device=self.mask.device, dtype=torch.float64)[:, None].expand(H, W)
+        return torch.where(self.mask.bool(), yy, torch.full_like(yy, float('nan')))
+
+
+def harmonic_basis(nangle: int, polar_dir: str, offset_angle: float):
+    """cos/sin of 2a and 4a computed by NumPy exactly as the reference does (PP:2983-2986, PP:2993)."""
+    pd = -1 if polar_dir == 'clockwise' else 1
+    alpha = pd * np.linspace(0, 180, nangle, endpoint=False) + offset_angle
+    e2 = np.exp(2j * np.deg2rad(alpha))
+    e4 = e2 ** 2
+    return [np.ascontiguousarray(x) for x in (e2.real, e2.imag, e4.real, e4.imag)]
+
+
+def rasterize_rois(rois: Sequence[dict], shape: Tuple[int, int], base_mask: Optional[np.ndarray] = None):
+    """Selected ROI polygons -> (roi_bits uint32 [H,W], ilow list, indices). Same rasteriser and the same
+    int32 truncation of the vertices as the reference (cv2.fillPoly, PP:2883-2889)."""
+    import cv2
+    sel = [r for r in (rois or []) if r.get('select')]
+    bits = np.zeros(shape, dtype=np.uint32)
+    if len(sel) > _cabi.PB_MAX_ROIS:
+        raise ValueError(f'at most {_cabi.PB_MAX_ROIS} selected ROIs per call')
+    tmp = np.zeros(shape, dtype=np.uint8)
+    for k, r in enumerate(sel):
+        verts = np.array([np.asarray(r['vertices']).T], dtype=np.int32)
+        tmp.fill(0)
+        cv2.fillPoly(tmp, verts, 1)
+        bits |= (tmp == 1).astype(np.uint32) << np.uint32(k)
+    if not sel:
+        bits[:] = 1
+    if base_mask is not None:
+        bits[np.asarray(base_mask) == 0] = 0
+    return bits, [float(r['ILow']) for r in sel], [r['indx'] for r in sel]
+
+
+def _ptr(t) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr() if isinstance(t, torch.Tensor) else t.ctypes.data
+
+
+class Engine:
+    """One analysis context per GPU."""
+
+    def __init__(self, device: Optional[int] = None):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError('polarimetry_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device('cuda', self.device_index)
+        self._ctx = C.c_void_p()
+        rc = self.lib.pb_create(C.byref(self._ctx), self.device_index)
+        if rc != 0:
+            raise _cabi.PbError('pb_create failed: ' + self.lib.pb_last_error(None).decode())
+        self._key_basis = self._key_calib = self._key_hist = self._key_rois = None
+
+    def close(self):
+        if getattr(self, '_ctx', None):
+            self.lib.pb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state upload -----------------------------------------------------------------------------
+    def _ck(self, rc, what):
+        _cabi.check(self.lib, self._ctx, rc, what)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _set_basis(self, N, p: AnalysisParams):
+        key = (N, p.polar_dir, float(p.offset_angle))
+        if key != self._key_basis:
+            c2, s2, c4, s4 = harmonic_basis(N, p.polar_dir, p.offset_angle)
+            self._ck(self.lib.pb_set_basis(self._ctx, N, _ptr(c2), _ptr(s2), _ptr(c4), _ptr(s4)), 'pb_set_basis')
+            self._key_basis = key
+
+    def _set_calib(self, p: AnalysisParams, calib: Optional[Calibration]):
+        if p.method == '1PF':
+            if calib is None or calib.rho_table is None:
+                raise ValueError('1PF needs a disk-cone Calibration')
+            key = ('disk', id(calib))
+            if key != self._key_calib:
+                n = calib.grid.size
+                self._ck(self.lib.pb_set_diskcone(self._ctx, _ptr(calib.rho_table), _ptr(calib.psi_table), n, _ptr(calib.grid)), 'pb_set_diskcone')
+                self._key_calib = key
+        elif p.method.startswith('4POLAR'):
+            if calib is None or calib.invKmat is None:
+                raise ValueError('4POLAR needs a K-matrix Calibration')
+            rows = int(p.method[-2]) + 1
+            if calib.invKmat.shape != (rows, 4):
+                raise ValueError('Error in the dimension of the calibration matrix')     # PC:451-452
+            self._ck(self.lib.pb_set_invk(self._ctx, _ptr(calib.invKmat), rows), 'pb_set_invk')
+
+    def _set_hist(self, p: AnalysisParams):
+        names = VAR_NAMES[p.method]
+        key = (p.method, p.nbins, tuple(p.ranges[n] for n in names))
+        if key != self._key_hist:
+            edges = np.ascontiguousarray(np.stack([np.linspace(p.ranges[n][0], p.ranges[n][1], p.nbins + 1) for n in names]))
+            is_rho = np.array([int(n == 'Rho') for n in names], dtype=np.int32)
+            self._ck(self.lib.pb_set_hist(self._ctx, len(names), p.nbins, _ptr(edges), _ptr(is_rho)), 'pb_set_hist')
+            self._key_hist = key
+
+    def _set_rois(self, ilows: Sequence[float], per_roi: bool):
+        n = len(ilows)
+        groups = [1 << k for k in range(n)] if (per_roi and n) else [0xffffffff]
+        key = (tuple(ilows), tuple(groups))
+        if key != self._key_rois:
+            il = np.asarray(ilows, dtype=np.float64)
+            gb = np.asarray(groups, dtype=np.uint32)
+            self._ck(self.lib.pb_set_rois(self._ctx, n, _ptr(il) if n else None, len(groups), _ptr(gb)), 'pb_set_rois')
+            self._key_rois = key
+        return len(groups)
+
+    def _params(self, p: AnalysisParams, dtype: str, N, H, W) -> PbParams:
+        flags = 0
+        if p.out_dtype == 'float64':
+            flags |= _cabi.FLAG_OUT_F64
+        if p.exact_chi2:
+            flags |= _cabi.FLAG_EXACT_CHI2
+        if p.force_unfused:
+            flags |= _cabi.FLAG_FORCE_UNFUSED
+        return PbParams(_cabi.METHODS[p.method], _cabi.DTYPES[dtype], N, H, W, int(p.bins[0]), int(p.bins[1]), flags,
+                        float(p.dark), float(p.removed_intensity), float(p.rotation[0]), float(p.rotation[1]),
+                        float(p.rotation[2]), float(p.chi2threshold), float(p.ilow))
+
+    def _to_device(self, a, dtype=None):
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device)
+        else:
+            a = np.ascontiguousarray(a)
+            if a.dtype == np.uint16:      # torch has limited uint16 support: move the bytes
+                t = torch.from_numpy(a.view(np.int16)).to(self.device).view(torch.uint16)
+            elif a.dtype == np.uint32:
+                t = torch.from_numpy(a.view(np.int32)).to(self.device)
+            else:
+                t = torch.from_numpy(a).to(self.device)
+        return t.contiguous() if dtype is None else t.to(dtype).contiguous()
+
+    @staticmethod
+    def _dtype_name(t: torch.Tensor) -> str:
+        name = str(t.dtype).replace('torch.', '')
+        if name not in _cabi.DTYPES:
+            raise TypeError(f'unsupported stack dtype {t.dtype}; use uint8, uint16, float32 or float64')
+        return name
+
+    # ---- the fused path ----------------------------------------------------------------------------
+    def analyze_batch(self, stacks, p: AnalysisParams, calib: Optional[Calibration] = None, rois: Optional[Sequence[dict]] = None,
+                      per_roi: bool = False, base_mask=None, edge_contours=None, want_intensity: bool = True,
+                      want_hist: bool = True, hist_per_stack: bool = False, out: Optional[dict] = None) -> dict:
+        """stacks [B,N,H,W] (device tensor or array). Returns dict of device tensors: 'vars' {name: [B,H,W]},
+        'intmap', 'mask', 'intensity' and 'hist' int64 [B or 1, n_groups, n_vars, nbins] (summed over the
+        batch unless hist_per_stack). Everything is enqueued on torch's current stream; nothing synchronises."""
+        t = self._to_device(stacks)
+        if t.dim() != 4:
+            raise ValueError('stacks must be [B,N,H,W]')
+        B, N, H, W = t.shape
+        names = VAR_NAMES[p.method]
+        if not p.method.startswith('4POLAR'):
+            self._set_basis(N, p)
+        self._set_calib(p, calib)
+        if want_hist:
+            self._set_hist(p)
+        bits_np, ilows, indices = (None, [], [])
+        roi_dev = None
+        if rois or base_mask is not None:
+            bits_np, ilows, indices = rasterize_rois(rois, (H, W), base_mask)
+            roi_dev = self._to_device(bits_np)
+        ng = self._set_rois(ilows, per_roi)
+        edge_dev = None if edge_contours is None else self._to_device(edge_contours, torch.float64)
+        pp = self._params(p, self._dtype_name(t), N, H, W)
+        if not want_hist:
+            pp.flags |= _cabi.FLAG_NO_HIST
+        mdt = torch.float64 if p.out_dtype == 'float64' else torch.float32
+        o = out if out is not None else {}
+        dev = self.device
+        if 'vars' not in o:
+            o['vars'] = {n: torch.empty((B, H, W), dtype=mdt, device=dev) for n in names}
+            o['intmap'] = torch.empty((B, H, W), dtype=mdt, device=dev)
+            o['mask'] = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+            o['intensity'] = torch.empty((B, H, W), dtype=torch.float64, device=dev) if want_intensity else None
+            if float(p.rotation[2]) != 0.0:
+                o['rho_angle'] = torch.empty((B, H, W), dtype=mdt, device=dev)
+            if edge_dev is not None:
+                o['rho_contour'] = torch.empty((B, H, W), dtype=mdt, device=dev)
+        nb = B if hist_per_stack else 1
+        if want_hist:
+            if 'hist' not in o:
+                o['hist'] = torch.zeros((nb, ng, len(names), p.nbins), dtype=torch.int64, device=dev)
+            else:
+                o['hist'].zero_()
+        outs = (PbOutputs * B)()
+        for b in range(B):
+            for k, n in enumerate(names):
+                outs[b].var[k] = o['vars'][n][b].data_ptr()
+            outs[b].intmap = o['intmap'][b].data_ptr()
+            outs[b].mask = o['mask'][b].data_ptr()
+            if o.get('intensity') is not None:
+                outs[b].intensity = o['intensity'][b].data_ptr()
+            if 'rho_angle' in o:
+                outs[b].rho_angle = o['rho_angle'][b].data_ptr()
+            if 'rho_contour' in o:
+                outs[b].rho_contour = o['rho_contour'][b].data_ptr()
+            if want_hist:
+                outs[b].hist = o['hist'][b if hist_per_stack else 0].data_ptr()
+        self._ck(self.lib.pb_analyze(self._ctx, C.byref(pp), t.data_ptr(), B, _ptr(roi_dev), _ptr(edge_dev), outs, self._stream()), 'pb_analyze')
+        o['plan'] = self.lib.pb_plan(self._ctx, C.byref(pp)).decode()
+        o['roi_indices'] = indices if (per_roi and indices) else [None]
+        o['roi_bits'] = bits_np
+        o['_keep'] = (t, roi_dev, edge_dev)
+        return o
+
+    def analyze(self, stack, p: AnalysisParams, calib: Optional[Calibration] = None, rois: Optional[Sequence[dict]] = None,
+                per_roi: bool = False, base_mask=None, edge_contours=None, want_hist: bool = True) -> Result:
+        """One stack [N,H,W] -> Result (maps on the device, histograms on the host)."""
+        t = self._to_device(stack)
+        o = self.analyze_batch(t[None], p, calib, rois, per_roi, base_mask, edge_contours, True, want_hist)
+        names = VAR_NAMES[p.method]
+        vars_ = [Variable(n, o['vars'][n][0]) for n in names]
+        rho = vars_[0].values
+        if 'rho_contour' in o:                                            # PP:3059-3068
+            edge = o['_keep'][2]
+            both = torch.isfinite(rho) & torch.isfinite(edge)
+            vars_.append(Variable('Rho_contour', o['rho_contour'][0]))
+            for v in list(vars_[1:-1]):
+                vars_.append(Variable(v.name + '_contour', torch.where(both, v.values, torch.full_like(v.values, float('nan')))))
+        if 'rho_angle' in o:                                              # PP:3069-3072
+            vars_.append(Variable('Rho_angle', o['rho_angle'][0]))
+        hist = {}
+        if want_hist:
+            h = o['hist'][0].cpu().numpy()
+            for g, idx in enumerate(o['roi_indices']):
+                for k, n in enumerate(names):
+                    hist[(n, idx)] = h[g, k]
+            # extra variables: standalone histogram kernel (PC:340-369)
+            for v in vars_[len(names):]:
+                if v.name in p.ranges:
+                    for g, idx in enumerate(o['roi_indices']):
+                        sel = None
+                        if o['roi_bits'] is not None:
+                            gb = (1 << g) if (per_roi and idx is not None) else 0xffffffff
+                            sel = self._to_device(((o['roi_bits'] & np.uint32(gb)) != 0).astype(np.uint8))
+                        hist[(v.name, idx)] = self.histo(v.values, sel, v.name, *p.ranges[v.name], float(p.rotation[1]), p.nbins)
+        return Result(vars_, o['intmap'][0], o['mask'][0], o['intensity'][0] if o.get('intensity') is not None else None,
+                      hist, o['roi_bits'], o['plan'])
+
+    def analyze_host(self, stacks_host, p: AnalysisParams, calib: Optional[Calibration] = None, out: Optional[dict] = None,
+                     want_hist: bool = True) -> dict:
+        """Host buffers in, host buffers out, through `pb_analyze_host` (H2D / kernels / D2H overlapped over two
+        streams). stacks_host: numpy array or pinned CPU tensor [B,N,H,W]. Returns dict of host arrays."""
+        a = stacks_host if isinstance(stacks_host, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(stacks_host).view(np.int16) if np.asarray(stacks_host).dtype == np.uint16 else np.ascontiguousarray(stacks_host))
+        src_dtype = 'uint16' if (not isinstance(stacks_host, torch.Tensor) and np.asarray(stacks_host).dtype == np.uint16) else self._dtype_name(a)
+        B, N, H, W = a.shape
+        names = VAR_NAMES[p.method]
+        if not p.method.startswith('4POLAR'):
+            self._set_basis(N, p)
+        self._set_calib(p, calib)
+        if want_hist:
+            self._set_hist(p)
+        ng = self._set_rois([], False)
+        pp = self._params(p, src_dtype, N, H, W)
+        if not want_hist:
+            pp.flags |= _cabi.FLAG_NO_HIST
+        mdt = torch.float64 if p.out_dtype == 'float64' else torch.float32
+        o = out if out is not None else {}
+        if 'vars' not in o:
+            pin = dict(pin_memory=True)
+            o['vars'] = {n: torch.empty((B, H, W), dtype=mdt, **pin) for n in names}
+            o['intmap'] = torch.empty((B, H, W), dtype=mdt, **pin)
+            o['mask'] = torch.empty((B, H, W), dtype=torch.uint8, **pin)
+            o['hist'] = torch.zeros((1, ng, len(names), p.nbins), dtype=torch.int64)
+        o['hist'].zero_()
+        outs = (PbOutputs * B)()
+        for b in range(B):
+            for k, n in enumerate(names):
+                outs[b].var[k] = o['vars'][n][b].data_ptr()
+            outs[b].intmap = o['intmap'][b].data_ptr()
+            outs[b].mask = o['mask'][b].data_ptr()
+            if want_hist:
+                outs[b].hist = o['hist'][0].data_ptr()
+        self._ck(self.lib.pb_analyze_host(self._ctx, C.byref(pp), a.data_ptr(), B, None, None, outs), 'pb_analyze_host')
+        return o
+
+    # ---- the individual seams ----------------------------------------------------------------------
+    def get_intensity(self, values, dark: float = 0.0, bin: Sequence[int] = (1, 1)) -> torch.Tensor:
+        """Stack.get_intensity (PC:260-264)."""
+        t = self._to_device(values)
+        N, H, W = t.shape
+        out = torch.empty((H, W), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.pb_get_intensity(self._ctx, t.data_ptr(), _cabi.DTYPES[self._dtype_name(t)], N, H, W, float(dark),
+                                           int(bin[0]), int(bin[1]), out.data_ptr(), self._stream()), 'pb_get_intensity')
+        return out
+
+    def field(self, values, p: AnalysisParams) -> torch.Tensor:
+        """analyze_stack's pre-processing + binning (PP:2953-2962) -> double field [N,H,W]."""
+        t = self._to_device(values)
+        N, H, W = t.shape
+        out = torch.empty((N, H, W), dtype=torch.float64, device=self.device)
+        pp = self._params(p, self._dtype_name(t), N, H, W)
+        self._ck(self.lib.pb_field(self._ctx, C.byref(pp), t.data_ptr(), out.data_ptr(), self._stream()), 'pb_field')
+        return out
+
+    def binning(self, field, bins: Sequence[int]) -> torch.Tensor:
+        """Polarimetry.binning (PP:2942-2946) on a double field [N,H,W]; returns a new tensor."""
+        t = self._to_device(field, torch.float64).clone()
+        N, H, W = t.shape
+        self._ck(self.lib.pb_binning(self._ctx, t.data_ptr(), N, H, W, int(bins[0]), int(bins[1]), self._stream()), 'pb_binning')
+        return t
+
+    def compute_fields(self, field, mask, p: AnalysisParams, calib: Optional[Calibration] = None, edge_contours=None,
+                       want_fit: bool = False, want_hist: bool = False) -> Result:
+        """compute_fields (PP:2981-3078) on an already pre-processed, binned double field and an incoming mask."""
+        f = self._to_device(field, torch.float64)
+        N, H, W = f.shape
+        m = self._to_device(np.asarray(mask, dtype=np.uint8) if not isinstance(mask, torch.Tensor) else mask.to(torch.uint8)).clone()
+        names = VAR_NAMES[p.method]
+        if not p.method.startswith('4POLAR'):
+            self._set_basis(N, p)
+        self._set_calib(p, calib)
+        if want_hist:
+            self._set_hist(p)
+        self._set_rois([], False)
+        pp = self._params(p, 'float64', N, H, W)
+        if not want_hist:
+            pp.flags |= _cabi.FLAG_NO_HIST
+        mdt = torch.float64 if p.out_dtype == 'float64' else torch.float32
+        dev = self.device
+        vars_ = [Variable(n, torch.empty((H, W), dtype=mdt, device=dev)) for n in names]
+        intmap = torch.empty((H, W), dtype=mdt, device=dev)
+        edge_dev = None if edge_contours is None else self._to_device(edge_contours, torch.float64)
+        o = PbOutputs()
+        for k, v in enumerate(vars_):
+            o.var[k] = v.values.data_ptr()
+        o.intmap = intmap.data_ptr()
+        o.mask = m.data_ptr()
+        extra = {}
+        if float(p.rotation[2]) != 0.0:
+            extra['Rho_angle'] = torch.empty((H, W), dtype=mdt, device=dev)
+            o.rho_angle = extra['Rho_angle'].data_ptr()
+        if edge_dev is not None:
+            extra['Rho_contour'] = torch.empty((H, W), dtype=mdt, device=dev)
+            o.rho_contour = extra['Rho_contour'].data_ptr()
+        hist_t = None
+        if want_hist:
+            hist_t = torch.zeros((1, len(names), p.nbins), dtype=torch.int64, device=dev)
+            o.hist = hist_t.data_ptr()
+        self._ck(self.lib.pb_compute_fields(self._ctx, C.byref(pp), f.data_ptr(), m.data_ptr(), None, _ptr(edge_dev), C.byref(o),
+                                            self._stream()), 'pb_compute_fields')
+        if 'Rho_contour' in extra:
+            both = torch.isfinite(vars_[0].values) & torch.isfinite(edge_dev)
+            base = list(vars_[1:])
+            vars_.append(Variable('Rho_contour', extra['Rho_contour']))
+            for v in base:
+                vars_.append(Variable(v.name + '_contour', torch.where(both, v.values, torch.full_like(v.values, float('nan')))))
+        if 'Rho_angle' in extra:
+            vars_.append(Variable('Rho_angle', extra['Rho_angle']))
+        res = Result(vars_, intmap, m, None, {}, None, 'compute_fields')
+        if want_hist:
+            h = hist_t.cpu().numpy()
+            res.hist = {(n, None): h[0, k] for k, n in enumerate(names)}
+        if want_fit and not p.method.startswith('4POLAR'):
+            fit = torch.empty_like(f)
+            chi2 = torch.empty((H, W), dtype=torch.float64, device=dev)
+            self._ck(self.lib.pb_fit_maps(self._ctx, C.byref(pp), f.data_ptr(), m.data_ptr(), fit.data_ptr(), chi2.data_ptr(),
+                                          self._stream()), 'pb_fit_maps')
+            res.field_fit, res.chi2 = fit, chi2
+        return res
+
+    def histo(self, values, sel, name: str, vmin: float, vmax: float, rotation: float = 0.0, nbins: int = 60,
+              htype: str = 'normal') -> np.ndarray:
+        """Numeric part of Variable.histo (PC:340-369): int64 counts[nbins]."""
+        v = self._to_device(values)
+        if v.dtype not in (torch.float32, torch.float64):
+            v = v.to(torch.float64)
+        s = None if sel is None else self._to_device(sel).to(torch.uint8).contiguous()
+        fold = htype == 'polar3'
+        edges = np.linspace(vmin, 90 if fold else vmax, nbins + 1)
+        counts = torch.zeros(nbins, dtype=torch.int64, device=self.device)
+        self._ck(self.lib.pb_histo(self._ctx, v.data_ptr(), int(v.dtype == torch.float64), _ptr(s), v.numel(),
+                                   int(name in ('Rho', 'Rho_angle')), float(rotation), int(fold), _ptr(edges), nbins,
+                                   counts.data_ptr(), self._stream()), 'pb_histo')
+        return counts.cpu().numpy()
+
+    def stats(self, values, rho, sel, circular: bool, rotation_fig: float = 0.0, rewrap: bool = False, fold90: bool = False):
+        """Reductions of return_vecexcel (PP:2744-2779) for one variable: dict(N, mean, std, mean_delta)."""
+        v = self._to_device(values)
+        r = None if rho is None else self._to_device(rho).to(v.dtype).contiguous()
+        s = None if sel is None else self._to_device(sel).to(torch.uint8).contiguous()
+        out = np.zeros(5)
+        code = int(circular) | (int(rewrap) << 1)
+        self._ck(self.lib.pb_stats(self._ctx, v.data_ptr(), _ptr(r), int(v.dtype == torch.float64), _ptr(s), v.numel(), code,
+                                   float(rotation_fig), int(fold90), _ptr(out), self._stream()), 'pb_stats')
+        return dict(N=int(out[0]), mean=out[1], std=out[2], mean_delta=out[3])
+
+    def roi_stats(self, res: Result, p: AnalysisParams, roi_index: Optional[int] = None, group: int = 0) -> Dict[str, float]:
+        """The numeric columns of return_vecexcel (PP:2739-2779) for one ROI (or the whole image)."""
+        sel = None
+        if res.roi_map is not None:
+            gb = np.uint32(1 << group) if roi_index is not None else np.uint32(0xffffffff)
+            sel = ((res.roi_map & gb) != 0).astype(np.uint8)
+        rho = res.vars[0].values
+        st = self.stats(rho, rho, sel, True, float(p.rotation[1]), rewrap=True)
+        out = {'N': st['N'], 'MeanRho': st['mean'], 'StdRho': st['std'], 'MeanDeltaRho': st['mean_delta']}
+        for v in res.vars[1:]:
+            if v.name in ('Rho_contour', 'Rho_angle'):
+                for tag, fold in (('180', False), ('90', True)):
+                    s2 = self.stats(v.values, rho, sel, True, 0.0, rewrap=False, fold90=fold)
+                    out[f'Mean{v.name}_{tag}'], out[f'Std{v.name}_{tag}'], out[f'MeanDelta{v.name}_{tag}'] = s2['mean'], s2['std'], s2['mean_delta']
+            else:
+                s2 = self.stats(v.values, rho, sel, False)
+                out['Mean' + v.name], out['Std' + v.name] = s2['mean'], s2['std']
+        s3 = self.stats(res.intmap, rho, sel, False)
+        out['MeanInt'], out['StdInt'] = s3['mean'], s3['std']
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.pb_launch_count(self._ctx))
+
+
+# ---- drop-in functions with the reference's signatures ---------------------------------------------------
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+def get_intensity(self, dark: float = 0.0, bin: List[int] = [1, 1]) -> np.ndarray:
+    """Drop-in for Stack.get_intensity (PC:260-264); `self` is a reference Stack."""
+    return default_engine().get_intensity(self.values, dark, [int(b) for b in bin]).cpu().numpy()
+
+
+def binning(self, field: np.ndarray) -> np.ndarray:
+    """Drop-in for Polarimetry.binning (PP:2942-2946); `self` is the reference application object."""
+    bins = [int(sb.get()) for sb in self.bin_spinboxes]
+    if any(s > 1 for s in bins):
+        return default_engine().binning(field, bins).cpu().numpy()
+    return field
+
+
+def compute_fields(field: np.ndarray, datastack, mask: np.ndarray, method: str = '1PF', polar_dir: str = 'clockwise',
+                   offset_angle: float = 0, calibration=None, edge_contours=None, reference_angle: float = 0,
+                   rotation: float = 0, for_calib: bool = False, chi2threshold: float = 500, _Variable=None):
+    """Drop-in for the module-level compute_fields (PP:2981-3078): same arguments, same side effects
+    (`mask` updated in place; `datastack.vars/.intmap/.xmap/.ymap/.field/.field_fit/.chi2` filled)."""
+    eng = default_engine()
+    p = AnalysisParams(method=method, polar_dir=polar_dir, offset_angle=float(offset_angle),
+                       rotation=(float(rotation), 0.0, float(reference_angle)), chi2threshold=float(chi2threshold))
+    cal = None
+    if method == '1PF':
+        cal = getattr(calibration, '_pb_calib', None)
+        if cal is None:
+            cal = Calibration(calibration.RhoPsi[:, :, 0], calibration.RhoPsi[:, :, 1], calibration.xy[0].size, name=getattr(calibration, 'name', ''))
+            try:
+                calibration._pb_calib = cal
+            except Exception:
+                pass
+    elif method.startswith('4POLAR'):
+        cal = Calibration(invK=calibration.invKmat)
+    res = eng.compute_fields(field, mask, p, cal, edge_contours, want_fit=not for_calib)
+    mk = (lambda n, v: _Variable(n, values=v)) if _Variable is not None else Variable
+    datastack.vars = [mk(v.name, v.values.cpu().numpy()) for v in res.vars]
+    final = res.mask.cpu().numpy().astype(bool)
+    mask[...] = final
+    datastack.intmap = res.intmap.cpu().numpy()
+    if for_calib:
+        return datastack
+    datastack.xmap, datastack.ymap = res.xmap.cpu().numpy(), res.ymap.cpu().numpy()
+    if edge_contours is not None:
+        both = np.isfinite(datastack.vars[0].values) & np.isfinite(edge_contours)
+        datastack.xct[~both], datastack.yct[~both] = np.nan, np.nan
+    if not method.startswith('4POLAR'):
+        field[:, ~final] = np.nan
+        datastack.field, datastack.field_fit, datastack.chi2 = field, res.field_fit.cpu().numpy(), res.chi2.cpu().numpy()
+    return datastack
+
+
+def install(pypolar_module, classes_module=None) -> None:
+    """Rebind the hot-path seams of an imported reference (`import PyPOLAR`) to this package."""
+    Var = getattr(pypolar_module, 'Variable', None)
+
+    def _cf(*a, **k):
+        return compute_fields(*a, _Variable=Var, **k)
+
+    pypolar_module.compute_fields = _cf
+    pypolar_module.Polarimetry.binning = binning
+    stack_cls = getattr(classes_module, 'Stack', None) or getattr(pypolar_module, 'Stack', None)
+    if stack_cls is not None:
+        stack_cls.get_intensity = get_intensity

@@ -1,0 +1,55 @@
+"""Build libpolarb200.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc.
+
+    python -m polarimetry_b200.build [--force]
+
+The library is compiled for B200 only (-gencode arch=compute_100a,code=sm_100a), with -fmad=false so that
+no fp64 multiply-add is contracted behind the arithmetic contract's back, and -lineinfo so ncu's source
+page maps to these files. nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / 'csrc'
+LIB = PKG / 'libpolarb200.so'
+SOURCES = ['pb_api.cu', 'pb_pixel.cu', 'pb_box.cu', 'pb_march.cu', 'pb_reduce.cu']
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
+              '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + list(CSRC.glob('*.cuh')) + [PKG.parent / 'include' / 'polar_b200.h']
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale():
+        return LIB
+    objs = []
+    (PKG / 'build').mkdir(exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = PKG / 'build' / (s + '.o')
+        cmd = ['nvcc', *NVCC_FLAGS, '-c', str(CSRC / s), '-o', str(o)] + (['-Xptxas', '-v'] if verbose else [])
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(o))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(f'--- {s}\n{out}\n')
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError('nvcc failed')
+    subprocess.check_call(['nvcc', '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', str(LIB), *objs])
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

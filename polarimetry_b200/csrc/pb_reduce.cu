@@ -1,0 +1,159 @@
+// pb_reduce.cu -- standalone histogram, ROI statistics and fit/chi2 map kernels.
+//
+// pb_histo   : numeric part of Variable.histo (pypolar_classes.py:340-369) on a finished map.
+// pb_stats   : the reductions of return_vecexcel (PyPOLAR.py:2744-2779): N, (circular) mean, std, mean delta.
+// pb_fit_maps: field_fit / chi2 for the individual-fit viewer (PP:2990-2999, PP:3073-3077), fp64, reference order.
+#include "pb_dev.cuh"
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_histo(const T *__restrict__ vals, const uint8_t *__restrict__ sel, long long n, int is_rho,
+                                               double rot_fig, int fold90, const double *__restrict__ edges, int nbins, double inv_w,
+                                               unsigned long long *__restrict__ counts) {
+    __shared__ unsigned cnt[PB_MAX_BINS];
+    __shared__ double e[PB_MAX_BINS + 1];
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) cnt[k] = 0u;
+    for (int k = threadIdx.x; k <= nbins; k += blockDim.x) e[k] = edges[k];
+    __syncthreads();
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        if (sel && !sel[p]) continue;
+        double d = (double)vals[p];
+        if (!pb_finite(d)) continue;
+        if (is_rho) d = pb_pymod(2.0 * (d + rot_fig), 360.0) / 2.0;
+        if (fold90 && d >= 90.0) d = 180.0 - d;
+        int b = pb_bin(d, e, nbins, inv_w);
+        if (b >= 0) atomicAdd(&cnt[b], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x)
+        if (cnt[k]) atomicAdd(counts + k, (unsigned long long)cnt[k]);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    }
+    return r;
+}
+
+constexpr double D2R = 3.141592653589793238462643383279502884 / 180.0;
+
+template <typename T>
+__device__ __forceinline__ bool stat_value(const T *vals, const T *rho, const uint8_t *sel, long long p, int circular, double rot_fig,
+                                           int rewrap, int fold90, double &d) {
+    if (sel && !sel[p]) return false;
+    if (rho && !pb_finite((double)rho[p])) return false;
+    d = (double)vals[p];
+    if (circular) {
+        if (!pb_finite(d)) return false;
+        if (rewrap) d = pb_pymod(2.0 * (d + rot_fig), 360.0) / 2.0;
+        if (fold90 && d >= 90.0) d = 180.0 - d;
+    }
+    return true;
+}
+
+// pass 1: acc[0] += count, acc[1] += sum d (or sum cos 2d), acc[2] += sum sin 2d
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats1(const T *vals, const T *rho, const uint8_t *sel, long long n, int circular, double rot_fig,
+                                                int rewrap, int fold90, double *acc) {
+    __shared__ double sh[8];
+    double c = 0.0, s1 = 0.0, s2 = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double d;
+        if (!stat_value(vals, rho, sel, p, circular, rot_fig, rewrap, fold90, d)) continue;
+        c += 1.0;
+        if (circular) { double sn, cs; sincos(2.0 * d * D2R, &sn, &cs); s1 += cs; s2 += sn; }
+        else s1 += d;
+    }
+    c = block_sum(c, sh); s1 = block_sum(s1, sh); s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) { atomicAdd(acc + 0, c); atomicAdd(acc + 1, s1); atomicAdd(acc + 2, s2); }
+}
+
+// pass 2: acc[3] += sum delta, acc[4] += sum delta^2, delta = wrapto180(2(d-mean))/2 (circular) or d - mean
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats2(const T *vals, const T *rho, const uint8_t *sel, long long n, int circular, double rot_fig,
+                                                int rewrap, int fold90, double mean, double *acc) {
+    __shared__ double sh[8];
+    double s1 = 0.0, s2 = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        double d;
+        if (!stat_value(vals, rho, sel, p, circular, rot_fig, rewrap, fold90, d)) continue;
+        double dl = circular ? remainder(2.0 * (d - mean), 360.0) / 2.0 : d - mean;
+        s1 += dl; s2 += dl * dl;
+    }
+    s1 = block_sum(s1, sh); s2 = block_sum(s2, sh);
+    if (threadIdx.x == 0) { atomicAdd(acc + 3, s1); atomicAdd(acc + 4, s2); }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(256) k_fit_maps(const double *__restrict__ f, const uint8_t *__restrict__ mask, long long P, int N,
+                                                  typename BasisSel<NH>::type bs, double *__restrict__ fit, double *__restrict__ chi2o) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const bool m = mask ? mask[p] != 0 : true;
+    double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double x = f[(long long)i * P + p];
+        S0 = S0 + x; Sc = Sc + x * bs.c2[i]; Ss = Ss + x * bs.s2[i];
+        if constexpr (NH == 2) { Sc4 = Sc4 + x * bs.c4[i]; Ss4 = Ss4 + x * bs.s4[i]; }
+    }
+    const double dN = (double)N, k2 = 2.0 / dN;
+    double a0 = S0 / dN;
+    if (a0 == 0.0) a0 = pb_nan();
+    const double a2r = k2 * Sc, a2i = k2 * Ss, a4r = k2 * Sc4, a4i = k2 * Ss4;
+    double acc = 0.0;
+    for (int i = 0; i < N; ++i) {
+        double ft = a0 + fma(a2r, bs.c2[i], a2i * bs.s2[i]);
+        if constexpr (NH == 2) ft = ft + fma(a4r, bs.c4[i], a4i * bs.s4[i]);
+        double d = f[(long long)i * P + p] - ft;
+        acc = acc + (d * d) / ft;
+        if (fit) fit[(long long)i * P + p] = m ? ft : pb_nan();
+    }
+    if (chi2o) chi2o[p] = m ? acc / dN : pb_nan();
+}
+
+}  // namespace
+
+cudaError_t pb_launch_histo(const void *vals, int is_f64, const uint8_t *sel, long long n, int is_rho, double rot_fig, int fold90,
+                            const double *edges_dev, int nbins, double inv_w, int64_t *counts, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256 < 148LL * 8 ? (n + 255) / 256 : 148LL * 8);
+    if (blocks < 1) blocks = 1;
+    if (is_f64) k_histo<double><<<blocks, 256, 0, st>>>((const double *)vals, sel, n, is_rho, rot_fig, fold90, edges_dev, nbins, inv_w, (unsigned long long *)counts);
+    else k_histo<float><<<blocks, 256, 0, st>>>((const float *)vals, sel, n, is_rho, rot_fig, fold90, edges_dev, nbins, inv_w, (unsigned long long *)counts);
+    return cudaGetLastError();
+}
+
+cudaError_t pb_launch_stats(int pass, const void *vals, const void *rho, int is_f64, const uint8_t *sel, long long n, int circular,
+                            double rot_fig, int rewrap, int fold90, double mean, double *acc, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256 < 148LL * 8 ? (n + 255) / 256 : 148LL * 8);
+    if (blocks < 1) blocks = 1;
+    if (is_f64) {
+        if (pass == 1) k_stats1<double><<<blocks, 256, 0, st>>>((const double *)vals, (const double *)rho, sel, n, circular, rot_fig, rewrap, fold90, acc);
+        else k_stats2<double><<<blocks, 256, 0, st>>>((const double *)vals, (const double *)rho, sel, n, circular, rot_fig, rewrap, fold90, mean, acc);
+    } else {
+        if (pass == 1) k_stats1<float><<<blocks, 256, 0, st>>>((const float *)vals, (const float *)rho, sel, n, circular, rot_fig, rewrap, fold90, acc);
+        else k_stats2<float><<<blocks, 256, 0, st>>>((const float *)vals, (const float *)rho, sel, n, circular, rot_fig, rewrap, fold90, mean, acc);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pb_launch_fit_maps(const double *f, const uint8_t *mask, long long P, int N, int nharm, const Basis2 &bs, double *fit,
+                               double *chi2, cudaStream_t st) {
+    unsigned blocks = (unsigned)((P + 255) / 256);
+    if (nharm == 1) {
+        Basis1 b1;
+        memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));
+        k_fit_maps<1><<<blocks, 256, 0, st>>>(f, mask, P, N, b1, fit, chi2);
+    } else {
+        k_fit_maps<2><<<blocks, 256, 0, st>>>(f, mask, P, N, bs, fit, chi2);
+    }
+    return cudaGetLastError();
+}

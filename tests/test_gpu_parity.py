@@ -1,0 +1,226 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors of the unmodified reference
+and against the oracle on the same seeded inputs. Bars: masks, intensity/intmap, histogram counts and all
+1PF maps BIT-EXACT (float64 outputs); rho/psi/eta within 1e-9 deg and S2/S4 within 1e-12 where a
+transcendental is involved (north_star asks 1e-3 deg); float32 output mode within 1e-3 deg."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, restate as rs
+from polarimetry_b200 import AnalysisParams, Calibration, Engine
+from tests import util
+
+pytestmark = pytest.mark.gpu
+NAMES = [c['name'] for c in util.CASES]
+ANGLE_VARS = ('Rho', 'Psi', 'Eta', 'Rho_angle', 'Rho_contour', 'Psi_contour', 'Eta_contour')
+
+
+@pytest.fixture(scope='module')
+def eng():
+    e = Engine()
+    yield e
+    e.close()
+
+
+_calibs = {}
+
+
+def calib_for(c):
+    key = (c['method'], c['disk'], c['calib_label'])
+    if key not in _calibs:
+        o = util.calib_for(c)
+        if o is None:
+            _calibs[key] = None
+        elif o.invK is not None:
+            _calibs[key] = Calibration(invK=o.invK, name=o.name)
+        else:
+            _calibs[key] = Calibration(o.rho_table, o.psi_table, o.grid.size, name=o.name)
+    return _calibs[key]
+
+
+def params_for(c, **kw):
+    return AnalysisParams(method=c['method'], dark=c['dark'], removed_intensity=c['removed_intensity'], bins=c['bins'],
+                          polar_dir=c['polar_dir'], offset_angle=c['offset_angle'], rotation=c['rotation'], ilow=c['ilow'],
+                          nbins=c['nbins'], **kw)
+
+
+def check_against_golden(c, res, g, exact_maps, tol_angle=1e-9, tol_other=1e-12, check_hist=True):
+    names = util.INDEX[c['name']]['var_order']
+    assert [v.name for v in res.vars] == names
+    assert util.eq(res.intensity.cpu().numpy(), g['intensity'])
+    assert util.eq(res.mask.cpu().numpy().astype(bool), np.isfinite(g['var_Rho']) & np.isfinite(g['intmap']))
+    im = res.intmap.cpu().numpy().astype(np.float64)
+    if exact_maps:
+        assert util.eq(im, g['intmap'])
+    else:
+        assert util.eq(np.isnan(im), np.isnan(g['intmap']))
+    for v in res.vars:
+        got = v.values.cpu().numpy().astype(np.float64)
+        ref = g['var_' + v.name]
+        assert util.eq(np.isnan(got), np.isnan(ref)), v.name
+        if exact_maps and c['method'] == '1PF':
+            assert util.eq(got, ref), v.name
+        else:
+            m = np.isfinite(ref)
+            d = util.circ_diff(got[m], ref[m]) if v.name.startswith('Rho') else np.abs(got[m] - ref[m])
+            assert d.max(initial=0.0) <= (tol_angle if v.name in ANGLE_VARS else tol_other), (v.name, d.max())
+    if check_hist:
+        for (k, s), h in res.hist.items():
+            assert util.eq(h, g[util.hist_key(k, s)]), (k, s)
+        assert len(res.hist) == len([k for k in g.files if k.startswith('hist_')])
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_analyze_matches_reference(eng, name):
+    c = util.CASE_BY_NAME[name]
+    g = util.golden(name)
+    edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
+    res = eng.analyze(g['values'], params_for(c), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    check_against_golden(c, res, g, exact_maps=True)
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_unfused_kernels_match_reference(eng, name):
+    c = util.CASE_BY_NAME[name]
+    g = util.golden(name)
+    edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
+    res = eng.analyze(g['values'], params_for(c, force_unfused=True), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    assert res.plan == 'unfused'
+    check_against_golden(c, res, g, exact_maps=True)
+
+
+@pytest.mark.parametrize('name', [n for n in NAMES if not n.startswith('4polar')])
+def test_exact_chi2_flag_gives_same_decisions(eng, name):
+    c = util.CASE_BY_NAME[name]
+    g = util.golden(name)
+    edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
+    res = eng.analyze(g['values'], params_for(c, exact_chi2=True), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    check_against_golden(c, res, g, exact_maps=True)
+
+
+@pytest.mark.parametrize('name', ['1pf_bin1x1', '1pf_bin3x3', '1pf_disk561_bin3', 'shg_bin1', 'cars_bin3', '4polar3d_bin1', '4polar2d_bin3'])
+def test_float32_output_mode(eng, name):
+    """Throughput mode: float32 maps (<= 1e-3 deg, north_star), histograms still from the fp64 values."""
+    c = util.CASE_BY_NAME[name]
+    g = util.golden(name)
+    res = eng.analyze(g['values'], params_for(c, out_dtype='float32'), calib_for(c), c['rois'], c['per_roi'])
+    assert res.vars[0].values.dtype == torch.float32
+    check_against_golden(c, res, g, exact_maps=False, tol_angle=1e-3, tol_other=1e-6)
+
+
+def test_seams_get_intensity_field_binning(eng):
+    for name in ('1pf_bin3x3', '1pf_bin2x5', 'cars_bin2x5', '1pf_u8', '1pf_fracdark'):
+        c = util.CASE_BY_NAME[name]
+        g = util.golden(name)
+        v = g['values']
+        p = util.params_for(c)
+        I = eng.get_intensity(v, c['dark'], c['bins']).cpu().numpy()
+        assert util.eq(I, g['intensity']), name
+        f_ref = rs.binning(rs.preprocess(v, p), c['bins'])
+        f = eng.field(v, params_for(c)).cpu().numpy()
+        assert util.eq(f, f_ref), name
+        f2 = eng.binning(rs.preprocess(v, p), c['bins']).cpu().numpy()
+        assert util.eq(f2, f_ref), name
+
+
+@pytest.mark.parametrize('shape,bins', [((1, 1, 1), (3, 3)), ((2, 1, 7), (5, 4)), ((1, 2, 3), (7, 7)), ((3, 70, 131), (20, 20)),
+                                        ((2, 33, 64), (32, 32)), ((1, 300, 257), (2, 3))])
+def test_box_filter_edge_shapes(eng, shape, bins):
+    from scipy.ndimage import uniform_filter
+    rng = np.random.default_rng(5)
+    f = rng.integers(0, 65535, size=shape).astype(np.float64) / 7.0
+    ref = uniform_filter(f, size=[0, bins[0], bins[1]], mode='reflect')
+    assert util.eq(eng.binning(f, bins).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize('name', ['1pf_bin3x3', '1pf_noncalib', 'shg_noncalib', '4polar3d_bin3', '1pf_adversarial_bin3'])
+def test_compute_fields_seam(eng, name):
+    """compute_fields on the oracle's double field + incoming mask (the S1 seam), incl. fit/chi2 maps."""
+    c = util.CASE_BY_NAME[name]
+    g = util.golden(name)
+    v = g['values']
+    p = util.params_for(c)
+    edge = cases.make_edge(v.shape[1:]) if c['edge'] else None
+    intensity = rs.get_intensity(v, p.dark, p.bins)
+    _, rmask = rs.roi_masks(intensity, p)
+    field = rs.binning(rs.preprocess(v, p), p.bins)
+    res = eng.compute_fields(field, rmask[0], params_for(c), calib_for(c), edge, want_fit=not name.startswith('4polar'))
+    res.intensity = torch.from_numpy(g['intensity'])
+    check_against_golden(c, res, g, exact_maps=True, check_hist=False)
+    if 'chi2' in g.files:
+        m = res.mask.cpu().numpy().astype(bool)
+        chi2 = res.chi2.cpu().numpy()
+        assert util.eq(np.isnan(chi2), np.isnan(g['chi2']))
+        assert np.allclose(chi2[m], g['chi2'][m], rtol=1e-12, atol=0)
+        if 'field_fit' in g.files:
+            assert np.allclose(res.field_fit.cpu().numpy()[:, m], g['field_fit'][:, m], rtol=1e-13, atol=0)
+
+
+def test_histo_and_stats_seams(eng):
+    c = util.CASE_BY_NAME['1pf_rois']
+    g = util.golden('1pf_rois')
+    p = util.params_for(c)
+    ref = rs.analyze_stack(g['values'], p, util.calib_for(c), c['rois'], True)
+    res = eng.analyze(g['values'], params_for(c), calib_for(c), c['rois'], True)
+    for gi, idx in enumerate([1, 2]):
+        sel = rs.slice_roi(ref['roi_map'], idx)
+        for nm, rot in (('Rho', 12.0), ('Psi', 0.0)):
+            vmin, vmax = p.ranges[nm]
+            want = rs.histo(ref['vars'][nm], sel, nm, vmin, vmax, rot, 45)[0]
+            got = eng.histo(res.get_var(nm).values, sel.astype(np.uint8), nm, vmin, vmax, rot, 45)
+            assert util.eq(got, want)
+        want = rs.histo(ref['vars']['Rho'], sel, 'Rho_contour', 0, 180, 0.0, 30, 'polar3')[0]
+        got = eng.histo(res.get_var('Rho').values, sel.astype(np.uint8), 'Rho_contour', 0, 180, 0.0, 30, 'polar3')
+        assert util.eq(got, want)
+        st_ref = rs.vecstats(ref, ref['roi_map'], p, idx)
+        st = eng.roi_stats(res, params_for(c), idx, gi)
+        assert st['N'] == st_ref['N']
+        for k in ('MeanRho', 'StdRho', 'MeanDeltaRho', 'MeanPsi', 'StdPsi', 'MeanInt', 'StdInt'):
+            assert abs(st[k] - st_ref[k]) <= 1e-9 * max(1.0, abs(st_ref[k])), (k, st[k], st_ref[k])
+            assert rs.fmt3(float(st[k])) == rs.fmt3(float(st_ref[k]))
+
+
+def test_batch_and_host_paths(eng):
+    from polarimetry_b200 import synth
+    B, N, H, W = 5, 18, 64, 96
+    stacks = np.stack([synth.stack_1pf(H, W, N, seed=100 + b) for b in range(B)])
+    c = util.CASE_BY_NAME['1pf_bin1x1']
+    cal = calib_for(c)
+    for bins in ((1, 1), (3, 3)):
+        p = AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=45000.0)
+        o = eng.analyze_batch(stacks, p, cal)
+        oh = eng.analyze_host(stacks, p, cal)
+        hsum = np.zeros((2, 60), dtype=np.int64)
+        for b in range(B):
+            ref = rs.analyze_stack(stacks[b], rs.Params(method='1PF', dark=480.0, bins=bins, ilow=45000.0), util.calib_for(c))
+            for nm in ('Rho', 'Psi'):
+                assert util.eq(o['vars'][nm][b].cpu().numpy(), ref['vars'][nm])
+                assert util.eq(oh['vars'][nm][b].numpy(), ref['vars'][nm])
+            assert util.eq(o['intmap'][b].cpu().numpy(), ref['intmap'])
+            assert util.eq(oh['mask'][b].numpy().astype(bool), ref['mask'])
+            hsum[0] += ref['hist'][('Rho', None)]
+            hsum[1] += ref['hist'][('Psi', None)]
+        assert util.eq(o['hist'][0, 0].cpu().numpy(), hsum)
+        assert util.eq(oh['hist'][0, 0].numpy(), hsum)
+
+
+def test_larger_stack_properties(eng):
+    """Full-size-ish (1024x1024x18) checks that need no CPU oracle run: fused == unfused == exact-chi2 bitwise,
+    histogram total == number of finite values, idempotence of a second run."""
+    from polarimetry_b200 import synth
+    v = synth.stack_1pf(1024, 1024, 18, seed=7)
+    cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
+    for bins in ((1, 1), (3, 3)):
+        p = AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=50000.0)
+        a = eng.analyze(v, p, cal)
+        b = eng.analyze(v, AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=50000.0, force_unfused=True), cal)
+        c2 = eng.analyze(v, AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=50000.0, exact_chi2=True), cal)
+        for x in (b, c2):
+            for va, vb in zip(a.vars, x.vars):
+                assert torch.equal(torch.nan_to_num(va.values, nan=-1.0), torch.nan_to_num(vb.values, nan=-1.0))
+            assert torch.equal(a.mask, x.mask)
+            for k in a.hist:
+                assert util.eq(a.hist[k], x.hist[k])
+        rho = a.vars[0].values
+        assert int(a.hist[('Rho', None)].sum()) == int(torch.isfinite(rho).sum())
+        assert 0 < int(a.mask.sum()) < v.shape[1] * v.shape[2]
