@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixel-angles/s of the fused PyPOLAR analysis path on B200 (BASELINE.json's metric).
+
+Workload (config.workload): batch mode of BASELINE.json configs[3] on one GPU's share: synthetic 1PF stacks
+2048x2048x18 uint16 (generator G1), dark 480, 3x3 binning, disk-cone LUT, intensity threshold,
+rho/psi/intensity maps (float32) + mask + rho/psi histograms (60 bins, from the fp64 values). A "step" is one
+pass of the hot path over the rank's batch of stacks resident in HBM (batch >> L2, so no flush is needed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--bin B] [--batch S] [--impl reference]
+
+N > 1: launched under torchrun, one rank per GPU, stacks sharded across ranks (weak scaling: fixed per-GPU
+batch), no data-path collective; the per-rank histograms are summed with one NCCL all-reduce per step,
+inside the timed region. Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H, W, N = 2048, 2048, 18
+DISK = ROOT / 'tests' / 'golden' / 'calib' / 'Disk_Ga0_Pa0_Ta0_Gb0_Pb0_Tb0_Gc0_Pc0_Tc0.npz'
+DARK, ILOW = 480.0, 40000.0
+OUT_BYTES_PER_PIXEL = 13      # rho f32 + psi f32 + intmap f32 + mask u8
+
+
+def measured_peak_gbs():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        return float(json.loads(f.read_text())['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == 'Active' for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm)}
+
+
+# ---- CPU side: the oracle restatement (== the reference's NumPy/SciPy statements) ---------------------------
+def _cpu_one(args):
+    seed, h, w, bins = args
+    from oracle import restate as rs
+    from polarimetry_b200 import synth
+    d = np.load(DISK)
+    cal = rs.Calib.from_disk(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
+    v = synth.stack_1pf(h, w, N, seed=seed)
+    t0 = time.perf_counter()
+    rs.analyze_stack(v, rs.Params(method='1PF', dark=DARK, bins=bins, ilow=ILOW), cal)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(bins, workers: int, h: int = 1024, w: int = 1024, per_worker: int = 1):
+    """Run the oracle on `workers*per_worker` stacks of h x w x 18 over a process pool; returns (Mpx-angles/s, seconds)."""
+    import multiprocessing as mp
+    jobs = [(1000 + k, h, w, bins) for k in range(workers * per_worker)]
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_one, [(0, 64, 64, bins)] * workers)          # import / warm-up, untimed
+        t0 = time.perf_counter()
+        pool.map(_cpu_one, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    return len(jobs) * h * w * N / dt / 1e6, dt
+
+
+def host_workers():
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    bins = (a.bin, a.bin)
+    workers = host_workers()
+    vals = []
+    for s in range(a.warmup + a.steps):
+        v, dt = cpu_sample(bins, workers)
+        if s >= a.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    sample = f'{workers} stacks 1024x1024x18 uint16 per step, one per worker process (oracle/restate.py = the reference\'s NumPy/SciPy statements)'
+    line = {'impl': 'reference', 'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': a.gpus, 'steps': a.steps,
+            'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(a, None),
+            'cpu_baseline': {'value': value, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_config(a, batch):
+    return {'workload': f'1PF batch of {H}x{W}x{N} uint16 stacks, dark {DARK:.0f}, bin {a.bin}x{a.bin}, disk-cone LUT (no distortion), '
+                        f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
+            'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--bin', type=int, default=int(os.environ.get('PB_BENCH_BIN', '3')))
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('PB_BENCH_BATCH', '16')), help='stacks resident per GPU')
+    ap.add_argument('--e2e-batch', type=int, default=4)
+    ap.add_argument('--impl', default='b200')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        return run_reference_arm(a)
+
+    import torch
+    import torch.distributed as dist
+    from polarimetry_b200 import AnalysisParams, Calibration, Engine, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    eng = Engine(local)
+    d = np.load(DISK)
+    cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
+    p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ILOW, out_dtype='float32')
+
+    # synthetic stacks: a few distinct seeded G1 stacks per rank, tiled to the resident batch (19 MB/stack of host RNG work each)
+    B = a.batch
+    ndistinct = min(B, 4)
+    base = [torch.from_numpy(synth.stack_1pf(H, W, N, seed=1000 * rank + k).view(np.int16)) for k in range(ndistinct)]
+    stacks = torch.empty((B, N, H, W), dtype=torch.int16, device=dev)
+    for b in range(B):
+        stacks[b].copy_(base[b % ndistinct])
+    stacks = stacks.view(torch.uint16)
+    out = {}
+    launches0 = eng.launch_count()
+
+    def step():
+        o = eng.analyze_batch(stacks, p, cal, want_intensity=False, out=out)
+        if world > 1:
+            dist.all_reduce(o['hist'])
+        return o
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = (eng.launch_count() - launches0) // max(a.warmup, 3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record()
+    for s in range(a.steps):
+        step()
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(a.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    px_angles_step = B * H * W * N * world
+    value = px_angles_step * a.steps / (total_ms * 1e-3) / 1e6
+    plan = out['plan']
+
+    # roofline of the dominant kernel: algorithmic bytes of one launch / its CUDA-event duration (median step)
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = B * (H * W * N * 2 + H * W * OUT_BYTES_PER_PIXEL)
+    kern_ms = float(np.median(step_ms))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'kernel': plan, 'algorithmic_bytes_per_launch': alg_bytes,
+                'note': 'one launch = the whole per-GPU batch; duration = median CUDA-event step time'
+                        + (' (unfused plan: the step is several launches; achieved is step-level)' if plan == 'unfused' else '')}
+    tfile = ROOT / 'profiles' / 'traffic.json'
+    if tfile.exists():
+        try:
+            tj = json.loads(tfile.read_text())
+            key = f'{plan}_bin{a.bin}'
+            if key in tj:
+                roofline['traffic'] = tj[key]['dram_bytes_per_stack'] * B
+                roofline['traffic_source'] = tj[key].get('source')
+        except Exception:
+            pass
+
+    # e2e: the same metric through the host-buffer API (pinned host stacks in, maps + mask + histograms back to the host)
+    Be = a.e2e_batch
+    host = torch.empty((Be, N, H, W), dtype=torch.int16).pin_memory()
+    for b in range(Be):
+        host[b].copy_(base[b % ndistinct])
+    host_u16 = host.view(torch.uint16)
+    hout = {}
+    for _ in range(2):
+        eng.analyze_host(host_u16, p, cal, out=hout)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(a.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ho = eng.analyze_host(host_u16, p, cal, out=hout)      # synchronous: returns when the results are in host memory
+        _ = int(ho['hist'].sum())
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = Be * H * W * N * world * e2e_steps / float(te.item()) / 1e6
+    e2e = {'value': e2e_val, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': Be * H * W * N * 2,
+           'd2h_bytes_per_step': Be * (H * W * OUT_BYTES_PER_PIXEL) + 2 * 60 * 8, 'stacks_per_step': Be,
+           'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        workers = host_workers()
+        v, dt = cpu_sample((a.bin, a.bin), workers)
+        cpu = {'value': v, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port',
+               'sample': f'{workers} stacks 1024x1024x18 (one per worker process) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
+    if rank == 0:
+        line = {'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+                'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                'data': 'synthetic', 'config': workload_config(a, B), 'plan': plan, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+                'gpu_launches': int(launches_per_step * a.steps), 'clocks': clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

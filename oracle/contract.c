@@ -293,3 +293,43 @@ void pc_hist(const double *X, const uint8_t *sel, long P, int is_rho, double rot
         counts[lo]++;
     }
 }
+
+/* ---- checks of the exact-arithmetic shortcuts the CUDA kernels use (tests/test_shortcuts.py) ------------ */
+static uint64_t rng_next(uint64_t *s) { *s ^= *s << 13; *s ^= *s >> 7; *s ^= *s << 17; return *s; }
+
+/* x / n == fma(x, hi, x*lo) with (hi, lo) the double-double reciprocal of n: returns the number of mismatches
+ * over `count` random doubles (mixed: integers, thirds, running sums) plus all integers below 2^20. */
+long pc_check_div_by_const(int n, long count, uint64_t seed) {
+    double d = (double)n, hi = 1.0 / d, lo = fma(-hi, d, 1.0) / d;
+    long bad = 0;
+    uint64_t s = seed ? seed : 88172645463325252ULL;
+    for (long k = 0; k < (1L << 20); ++k) {
+        double x = (double)k;
+        if (fma(x, hi, x * lo) != x / d) ++bad;
+    }
+    for (long k = 0; k < count; ++k) {
+        uint64_t r = rng_next(&s);
+        double x;
+        switch (k & 3) {
+        case 0: x = (double)(r >> 11) * (1.0 / 9007199254740992.0) * 1048576.0; break;      /* uniform [0, 2^20) */
+        case 1: x = (double)(r % 16777216ULL) / 3.0 + (double)((r >> 32) % 65536ULL) / 7.0; break;
+        case 2: x = ldexp((double)(r >> 11), (int)(r % 80) - 60); break;                      /* wide exponent range */
+        default: x = (double)(r % 4294967296ULL) / (double)((r >> 40) % 20 + 1); break;
+        }
+        if (fma(x, hi, x * lo) != x / d) ++bad;
+    }
+    return bad;
+}
+
+/* RN(f * c) == fma(2^52 + f, c, -(2^52 * c)) for integers 0 <= f < 2^32: mismatches over all f < 2^16 and random f */
+long pc_check_magic_product(double c, long count, uint64_t seed) {
+    long bad = 0;
+    uint64_t s = seed ? seed : 1234567ULL;
+    const double T = 4503599627370496.0, k = -(T * c);
+    for (long f = 0; f < 65536 + count; ++f) {
+        double fv = f < 65536 ? (double)f : (double)(rng_next(&s) % 4294967296ULL);
+        double a = fma(T + fv, c, k), b = fv * c;
+        if (a != b && !(a == 0.0 && b == 0.0)) ++bad;
+    }
+    return bad;
+}

@@ -28,6 +28,15 @@ cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params 
 
 static std::string g_create_error;
 
+// double-double reciprocal of a small positive integer: hi = RN(1/n), lo = RN(1/n - hi) (exact residual via fma)
+void pb_ddrecip(int n, double *hi, double *lo) {
+    const double d = (double)n;
+    const double h = 1.0 / d;
+    const double r = std::fma(-h, d, 1.0);   // exact: 1 - h*d
+    *hi = h;
+    *lo = r / d;
+}
+
 struct pb_ctx {
     int device = 0;
     std::string err;
@@ -164,6 +173,11 @@ int pb_set_basis(pb_ctx *ctx, int N, const double *c2, const double *s2, const d
     memcpy(ctx->basis.c2, c2, sizeof(double) * N);
     memcpy(ctx->basis.s2, s2, sizeof(double) * N);
     if (c4 && s4) { memcpy(ctx->basis.c4, c4, sizeof(double) * N); memcpy(ctx->basis.s4, s4, sizeof(double) * N); }
+    for (int i = 0; i < N; ++i) {
+        const double T = 4503599627370496.0;   // 2^52: the products are exact (power-of-two scaling)
+        ctx->basis.kc2[i] = -(T * ctx->basis.c2[i]); ctx->basis.ks2[i] = -(T * ctx->basis.s2[i]);
+        ctx->basis.kc4[i] = -(T * ctx->basis.c4[i]); ctx->basis.ks4[i] = -(T * ctx->basis.s4[i]);
+    }
     ctx->basis_n = N;
     // the chi2 screening relies on {1, cos2a, sin2a, cos4a, sin4a} being orthogonal with norms N, N/2, ...
     const double *v[5] = {nullptr, ctx->basis.c2, ctx->basis.s2, ctx->basis.c4, ctx->basis.s4};
@@ -244,6 +258,13 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     a.hist_is_rho = ctx->is_rho_bits;
     a.sub = p->dark + p->removed_intensity; a.dark = p->dark;
     a.rot_stick = p->rotation_stick; a.rot_fig = p->rotation_fig; a.ref_angle = p->reference_angle; a.chi2thr = p->chi2_threshold;
+    pb_ddrecip(p->N, &a.invN_hi, &a.invN_lo);
+    a.k2 = 2.0 / (double)p->N;
+    a.dN = (double)p->N;
+    a.thr_lo_n = (float)(p->chi2_threshold * p->N * (1.0 - 1e-5));
+    a.thr_hi_n = (float)(p->chi2_threshold * p->N * (1.0 + 1e-5));
+    // the screening identity needs N >= 3 (second harmonic) / N >= 5 (fourth harmonic) equally spaced angles
+    if (p->N < (p->method == PB_1PF ? 3 : 5)) a.flags |= PB_FLAG_EXACT_CHI2;
     for (int v = 0; v < PB_MAX_VARS; ++v) a.inv_bin_width[v] = ctx->inv_w[v];
     for (int r = 0; r < PB_MAX_ROIS; ++r) { a.roi_ilow[r] = ctx->roi_ilow[r]; a.group_bits[r] = ctx->group_bits[r]; }
     if (ctx->n_rois == 0) a.roi_ilow[0] = p->ilow;
@@ -472,7 +493,8 @@ int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, in
     const int nv = method_nvars(p->method);
     const int nhist = ctx->n_groups * nv * (ctx->nbins > 0 ? ctx->nbins : 1);
     // device staging per pipeline slot: stack | maps (vars, intmap, rho_angle, rho_contour) | intensity | mask | hist
-    const size_t per_slot = sbytes + (size_t)(nv + 3) * P * msz + P * 8 + P + 256 + sizeof(int64_t) * nhist + 1024;
+    auto al = [](size_t n) { return (n + 255) & ~(size_t)255; };
+    const size_t per_slot = al(sbytes) + (size_t)(nv + 3) * al(P * msz) + al(P * 8) + al(P) + al(sizeof(int64_t) * nhist);
     if ((rc = ws_reserve(ctx, 5, 2 * per_slot + (size_t)P * 12 + 64))) return rc;
     char *base = (char *)ctx->ws[5];
     uint32_t *roi_dev = nullptr;

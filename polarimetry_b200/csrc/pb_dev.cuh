@@ -12,8 +12,14 @@
 
 #define PB_MAX_ANGLES 180
 
-struct Basis1 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES]; };
-struct Basis2 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES], c4[PB_MAX_ANGLES], s4[PB_MAX_ANGLES]; };
+// harmonic basis (host computed, PP:2983-2986 / PP:2993) and k* = -(2^52 * c), the exact constants of the
+// one-instruction rounded product RN(f c) = fma(2^52 + f, c, k) used on the integer fast path
+struct Basis1 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES], kc2[PB_MAX_ANGLES], ks2[PB_MAX_ANGLES]; };
+struct Basis2 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES], c4[PB_MAX_ANGLES], s4[PB_MAX_ANGLES],
+                       kc2[PB_MAX_ANGLES], ks2[PB_MAX_ANGLES], kc4[PB_MAX_ANGLES], ks4[PB_MAX_ANGLES]; };
+#ifndef PB_PIXEL_MIN_BLOCKS
+#define PB_PIXEL_MIN_BLOCKS 5
+#endif
 template <int NH> struct BasisSel { using type = Basis1; };
 template <> struct BasisSel<2> { using type = Basis2; };
 
@@ -39,6 +45,8 @@ struct PixArgs {
     unsigned hist_is_rho;       // bit v set: variable v is re-wrapped before binning
     double sub, dark;           // sub = dark + removed_intensity
     double rot_stick, rot_fig, ref_angle, chi2thr;
+    double invN_hi, invN_lo, k2, dN;   // double-double 1/N, 2.0/N, (double)N (host computed)
+    float thr_lo_n, thr_hi_n;          // chi2 threshold * N with -/+ 1e-5 margins (screening)
     double inv_bin_width[PB_MAX_VARS];
     double roi_ilow[PB_MAX_ROIS];
     uint32_t group_bits[PB_MAX_ROIS];

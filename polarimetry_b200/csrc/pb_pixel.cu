@@ -1,4 +1,4 @@
-// pb_pixel.cu -- per-pixel analysis kernels (no spatial coupling): harmonic projection, fit/chi2
+// pb_pixel.cu -- fused per-pixel analysis kernels (no spatial coupling): harmonic projection, fit/chi2
 // decisions, disk-cone LUT inversion, 4-harmonic outputs, 4POLAR inversion, threshold/ROI mask and
 // per-CTA shared-memory histograms.
 //
@@ -6,251 +6,236 @@
 // stack read once, maps + histograms out) and (b) as the last stage of the unfused path (double field in).
 // Replaces compute_fields, PyPOLAR.py:2981-3078, plus the mask logic of PP:2891/PP:2967 and the
 // histogram of pypolar_classes.py:340-369. Arithmetic order follows oracle/contract.c.
-#include "pb_dev.cuh"
+#include <type_traits>
+#include "pb_pixel.cuh"
 
 namespace {
 
-struct HistSmem {
-    // [n_groups][n_vars][nbins] counters followed by the edges; carved from dynamic shared memory
-    unsigned *cnt;
-    double *edges;
+// raw packed loads of PX consecutive integer elements (no unpacking: fewer live registers while in flight)
+template <typename UT, int PX> struct RawLoad;
+template <typename UT> struct RawLoad<UT, 1> {
+    static constexpr int WORDS = 1;
+    __device__ static __forceinline__ void ld(const UT *p, unsigned *w) { w[0] = (unsigned)__ldg(p); }
+    __device__ static __forceinline__ unsigned get(const unsigned *w, int) { return w[0]; }
+};
+template <> struct RawLoad<uint16_t, 4> {
+    static constexpr int WORDS = 2;
+    __device__ static __forceinline__ void ld(const uint16_t *p, unsigned *w) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        w[0] = r.x; w[1] = r.y;
+    }
+    __device__ static __forceinline__ unsigned get(const unsigned *w, int k) { return (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu); }
+};
+template <> struct RawLoad<uint8_t, 4> {
+    static constexpr int WORDS = 1;
+    __device__ static __forceinline__ void ld(const uint8_t *p, unsigned *w) { w[0] = __ldg(reinterpret_cast<const unsigned *>(p)); }
+    __device__ static __forceinline__ unsigned get(const unsigned *w, int k) { return (w[0] >> (8 * k)) & 0xffu; }
 };
 
-__device__ __forceinline__ HistSmem hist_setup(const PixArgs &a, unsigned char *smem) {
-    HistSmem h;
-    int ne = a.n_vars * (a.nbins + 1);
-    h.edges = reinterpret_cast<double *>(smem);
-    h.cnt = reinterpret_cast<unsigned *>(smem + sizeof(double) * ne);
-    int nc = a.n_groups * a.n_vars * a.nbins;
-    for (int k = threadIdx.x; k < ne; k += blockDim.x) h.edges[k] = a.hist_edges[k];
-    for (int k = threadIdx.x; k < nc; k += blockDim.x) h.cnt[k] = 0u;
-    __syncthreads();
-    return h;
+constexpr int CH = 6;   // angle planes per software-pipelined chunk
+
+template <typename UT, int PX> struct IntState {
+    double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX];
+    unsigned S0[PX], Ii[PX];
+    unsigned long long Sff[PX];
+};
+
+template <typename UT, int PX, bool FULL>
+__device__ __forceinline__ void load_chunk(const UT *&ptr, long long P, unsigned (&buf)[CH][RawLoad<UT, PX>::WORDS], int cnt) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+        if (FULL || j < cnt) { RawLoad<UT, PX>::ld(ptr, buf[j]); ptr += P; }
 }
 
-__device__ __forceinline__ void hist_flush(const PixArgs &a, const HistSmem &h, int64_t *dst) {
-    __syncthreads();
-    int nc = a.n_groups * a.n_vars * a.nbins;
-    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
-        unsigned c = h.cnt[k];
-        if (c) atomicAdd(reinterpret_cast<unsigned long long *>(dst) + k, (unsigned long long)c);
+// one chunk of the projection on the integer fast path: per pixel-angle one unpack, one fused subtract/clamp,
+// integer S0 and sum f^2, and per harmonic component ONE DFMA (the rounded product RN(f c) = fma(2^52+f, c, -(2^52 c)))
+// plus ONE DADD (the reference's separately rounded accumulation, PP:2989 / einsum).
+template <typename UT, int NH, int PX, bool FULL, typename Basis>
+__device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigned (&buf)[CH][RawLoad<UT, PX>::WORDS], const Basis &bs,
+                                              int i0, int cnt, int isub, int idark, bool sep) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+        if (FULL || j < cnt) {
+            const int i = i0 + j;
+            const double c2 = bs.c2[i], s2 = bs.s2[i], kc2 = bs.kc2[i], ks2 = bs.ks2[i];
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                const int v = (int)RawLoad<UT, PX>::get(buf[j], k);
+                const int f = max(v - isub, 0);
+                if (sep) s.Ii[k] += (unsigned)max(v - idark, 0);
+                s.S0[k] += (unsigned)f;
+                s.Sff[k] += (unsigned long long)((unsigned)f) * (unsigned)f;
+                const double X = __hiloint2double(0x43300000, f);   // 2^52 + f, exact
+                s.Sc[k] = s.Sc[k] + fma(X, c2, kc2);
+                s.Ss[k] = s.Ss[k] + fma(X, s2, ks2);
+                if constexpr (NH == 2) {
+                    s.Sc4[k] = s.Sc4[k] + fma(X, bs.c4[i], bs.kc4[i]);
+                    s.Ss4[k] = s.Ss4[k] + fma(X, bs.s4[i], bs.ks4[i]);
+                }
+            }
+        }
     }
 }
 
-__device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, int var, double val, uint32_t bits) {
-    if (!pb_finite(val)) return;
-    double d = val;
-    if ((a.hist_is_rho >> var) & 1u) d = pb_pymod(2.0 * (d + a.rot_fig), 360.0) / 2.0;
-    int b = pb_bin(d, h.edges + var * (a.nbins + 1), a.nbins, a.inv_bin_width[var]);
-    if (b < 0) return;
-    for (int g = 0; g < a.n_groups; ++g)
-        if (bits & a.group_bits[g]) atomicAdd(&h.cnt[(g * a.n_vars + var) * a.nbins + b], 1u);
+// vector stores of 4 consecutive pixels
+__device__ __forceinline__ void store4(void *base, long long p, double x0, double x1, double x2, double x3, bool f64) {
+    if (!base) return;
+    if (f64) {
+        double2 *d = reinterpret_cast<double2 *>(reinterpret_cast<double *>(base) + p);
+        d[0] = make_double2(x0, x1); d[1] = make_double2(x2, x3);
+    } else {
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(base) + p) = make_float4((float)x0, (float)x1, (float)x2, (float)x3);
+    }
 }
-
-template <typename OUT> __device__ __forceinline__ void store_map(void *base, long long p, double v) {
-    if (base) reinterpret_cast<OUT *>(base)[p] = (OUT)v;
-}
-__device__ __forceinline__ void store_any(void *base, long long p, double v, bool f64) {
-    if (f64) store_map<double>(base, p, v); else store_map<float>(base, p, v);
-}
-
-// threshold / ROI test, PP:2891 + PP:2967: any_r( bit_r & I >= ILow_r )
-__device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double I) {
-    if (a.n_rois == 0) return (bits != 0u) && (I >= a.roi_ilow[0]);
-    bool ok = false;
-    for (int r = 0; r < a.n_rois; ++r) ok |= ((bits >> r) & 1u) && (I >= a.roi_ilow[r]);
-    return ok;
-}
-
-// disk-cone LUT cell: g[i] <= x < g[i+1], last cell closed (scipy RegularGridInterpolator rule)
-__device__ __forceinline__ int lut_cell(const double *g, int n, double x) {
-    int k = (int)floor((x + 1.0) * (0.5 * (double)(n - 1)));
-    k = max(0, min(k, n - 2));
-    while (k > 0 && x < __ldg(g + k)) --k;
-    while (k < n - 2 && x >= __ldg(g + k + 1)) ++k;
-    return k;
-}
-
-__device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y, double &rho, double &psi) {
-    rho = pb_nan(); psi = pb_nan();
-    const double *g = a.grid;
-    const int n = a.lut_n;
-    double g0 = __ldg(g), g1 = __ldg(g + n - 1);
-    if (!(x >= g0 && x <= g1 && y >= g0 && y <= g1)) return;   // also rejects NaN
-    int i0 = lut_cell(g, n, x), i1 = lut_cell(g, n, y);
-    double ga = __ldg(g + i0), gb = __ldg(g + i0 + 1), gc = __ldg(g + i1), gd = __ldg(g + i1 + 1);
-    double t0 = (x - ga) / (gb - ga), t1 = (y - gc) / (gd - gc);
-    double u0 = 1.0 - t0, u1 = 1.0 - t1;
-    double w00 = (1.0 * u0) * u1, w01 = (1.0 * u0) * t1, w10 = (1.0 * t0) * u1, w11 = (1.0 * t0) * t1;
-    const double2 *T = a.lut;
-    double2 v00 = __ldg(T + (long long)i0 * n + i1), v01 = __ldg(T + (long long)i0 * n + i1 + 1);
-    double2 v10 = __ldg(T + (long long)(i0 + 1) * n + i1), v11 = __ldg(T + (long long)(i0 + 1) * n + i1 + 1);
-    double r = 0.0, q = 0.0;
-    r = r + v00.x * w00; r = r + v01.x * w01; r = r + v10.x * w10; r = r + v11.x * w11;
-    q = q + v00.y * w00; q = q + v01.y * w01; q = q + v10.y * w10; q = q + v11.y * w11;
-    rho = r; psi = q;
-}
-
-constexpr double RAD2DEG = 180.0 / 3.141592653589793238462643383279502884;
-constexpr double DEG2RAD = 3.141592653589793238462643383279502884 / 180.0;
 
 // ---------------------------------------------------------------------------------------------------
-// Harmonic modalities (1PF: NH=1, CARS/SRS/SHG/2PF: NH=2). One thread = PX consecutive pixels.
-template <typename T, int NH, int PX>
-__global__ void __launch_bounds__(256) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
+// Fused per-pixel kernel, harmonic modalities (1PF: NH=1, CARS/SRS/SHG/2PF: NH=2). One thread = PX
+// consecutive pixels; angle planes are streamed CH at a time with the next chunk's loads in flight.
+//   MODE 1: integer fast path -- uint8/uint16 stack, integer-valued dark and dark+removed, no sqrt.
+//   MODE 0: generic -- fp64 pre-processing (float input, fractional dark, CARS sqrt, or an already binned double field).
+template <typename T, int NH, int PX, int MODE>
+__global__ void __launch_bounds__(128, PB_PIXEL_MIN_BLOCKS) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0;
+    const pb_outputs out = a.outs[blockIdx.y];
+    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
     HistSmem hs;
+    hs.cnt = nullptr; hs.edges = nullptr;
     if (do_hist) hs = hist_setup(a, smem);
-    const int stack = blockIdx.y;
-    const pb_outputs out = a.outs[stack];
     const long long P = a.P;
     const long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PX;
-    const bool out64 = a.flags & PB_FLAG_OUT_F64;
     if (p0 < P) {
-        const T *base = reinterpret_cast<const T *>(a.stack) + (long long)stack * a.stack_stride + p0;
+        const T *base = reinterpret_cast<const T *>(a.stack) + (long long)blockIdx.y * a.stack_stride + p0;
         const int N = a.N;
-        const bool pre = !a.from_field;
-        const bool sep_int = pre && !a.intensity_in && (a.do_sqrt || a.sub != a.dark);
-        double S0[PX], Sc[PX], Ss[PX], Sc4[PX], Ss4[PX], Sff[PX], Isum[PX];
+        double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX], S0d[PX], Sffd[PX], Id[PX];
+        if constexpr (MODE == 1) {
+            using UT = typename std::conditional<std::is_same<T, uint8_t>::value, uint8_t, uint16_t>::type;
+            const UT *ptr = reinterpret_cast<const UT *>(base);
+            const int isub = (int)a.sub, idark = (int)a.dark;
+            const bool sep = isub != idark;
+            IntState<UT, PX> s;
 #pragma unroll
-        for (int k = 0; k < PX; ++k) { S0[k] = Sc[k] = Ss[k] = Sc4[k] = Ss4[k] = Sff[k] = Isum[k] = 0.0; }
-#pragma unroll 6
-        for (int i = 0; i < N; ++i) {
-            double v[PX];
-            VecLoad<T, PX>::ld(base + (long long)i * P, v);
-            const double c2 = bs.c2[i], s2 = bs.s2[i];
+            for (int k = 0; k < PX; ++k) { s.Sc[k] = s.Ss[k] = s.Sc4[k] = s.Ss4[k] = 0.0; s.S0[k] = s.Ii[k] = 0u; s.Sff[k] = 0ull; }
+            unsigned A[CH][RawLoad<UT, PX>::WORDS], B[CH][RawLoad<UT, PX>::WORDS];
+            int i = 0;
+            if (N >= CH) load_chunk<UT, PX, true>(ptr, P, A, CH); else load_chunk<UT, PX, false>(ptr, P, A, N);
+            // ping-pong: A holds angles [i, i+nA), B is loaded while A is consumed, and vice versa
+            while (true) {
+                const int nA = min(CH, N - i), nB = min(CH, N - i - nA);
+                if (nB == CH) load_chunk<UT, PX, true>(ptr, P, B, CH); else load_chunk<UT, PX, false>(ptr, P, B, nB);
+                if (nA == CH) compute_chunk<UT, NH, PX, true>(s, A, bs, i, CH, isub, idark, sep);
+                else compute_chunk<UT, NH, PX, false>(s, A, bs, i, nA, isub, idark, sep);
+                i += nA;
+                if (i >= N) break;
+                const int nA2 = min(CH, N - i - nB);
+                if (nA2 == CH) load_chunk<UT, PX, true>(ptr, P, A, CH); else load_chunk<UT, PX, false>(ptr, P, A, nA2);
+                if (nB == CH) compute_chunk<UT, NH, PX, true>(s, B, bs, i, CH, isub, idark, sep);
+                else compute_chunk<UT, NH, PX, false>(s, B, bs, i, nB, isub, idark, sep);
+                i += nB;
+                if (i >= N) break;
+            }
 #pragma unroll
             for (int k = 0; k < PX; ++k) {
-                double f = v[k];
-                if (pre) {
-                    if (sep_int) Isum[k] = Isum[k] + pb_max0(v[k] - a.dark);
-                    f = pb_max0(f - a.sub);
-                    if (a.do_sqrt) f = sqrt(f);
-                }
-                S0[k] = S0[k] + f;
-                Sc[k] = Sc[k] + f * c2;
-                Ss[k] = Ss[k] + f * s2;
-                if constexpr (NH == 2) {
-                    Sc4[k] = Sc4[k] + f * bs.c4[i];
-                    Ss4[k] = Ss4[k] + f * bs.s4[i];
-                }
-                Sff[k] = fma(f, f, Sff[k]);   // screening only (not parity relevant)
+                Sc[k] = s.Sc[k]; Ss[k] = s.Ss[k]; Sc4[k] = s.Sc4[k]; Ss4[k] = s.Ss4[k];
+                S0d[k] = (double)s.S0[k];
+                Sffd[k] = (double)s.Sff[k];
+                Id[k] = sep ? (double)s.Ii[k] : S0d[k];
             }
-        }
-        const double dN = (double)N, k2 = 2.0 / dN;
-        bool need_exact[PX], harm_ok[PX];
-        double a0[PX], a2r[PX], a2i[PX], a4r[PX], a4i[PX];
-        bool any_exact = false;
+        } else {
+            const bool pre = !a.from_field;
+            const bool sep_int = pre && !a.intensity_in && (a.do_sqrt || a.sub != a.dark);
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            a0[k] = S0[k] / dN;
-            if (a0[k] == 0.0) a0[k] = pb_nan();
-            a2r[k] = k2 * Sc[k]; a2i[k] = k2 * Ss[k];
-            a4r[k] = k2 * Sc4[k]; a4i[k] = k2 * Ss4[k];
-            // Certified screening of (all fit_i > 0) & (chi2 <= thr) & (chi2 > 0) from the orthogonality identity
-            //   sum_i (f_i - fit_i)^2 = sum f^2 - N (a0^2 + |a2|^2/2 + |a4|^2/2),  a0 - |a2| - |a4| <= fit_i <= a0 + |a2| + |a4|.
-            // Undecided pixels (and N too small for the identity) replay the reference's fp64 loop below.
-            need_exact[k] = true; harm_ok[k] = false;
-            if (!(a.flags & PB_FLAG_EXACT_CHI2) && N >= (NH == 2 ? 5 : 3) && pb_finite(a0[k])) {
-                double q2 = a2r[k] * a2r[k] + a2i[k] * a2i[k], q4 = a4r[k] * a4r[k] + a4i[k] * a4i[k];
-                double amp = sqrt(q2) + (NH == 2 ? sqrt(q4) : 0.0);
-                double model = dN * (a0[k] * a0[k] + 0.5 * (q2 + (NH == 2 ? q4 : 0.0)));
-                double sse = Sff[k] - model;
-                double err = 1e-11 * (Sff[k] + model);
-                double fmin = a0[k] - amp * (1.0 + 1e-9), fmax = a0[k] + amp * (1.0 + 1e-9);
-                if (fmin > 1e-9 * a0[k] && pb_finite(fmax)) {
-                    double hi = (sse + err) / (dN * fmin) * (1.0 + 1e-9);
-                    double lo = (sse - err) / (dN * fmax) * (1.0 - 1e-9);
-                    if (hi <= a.chi2thr && lo > 0.0) { need_exact[k] = false; harm_ok[k] = true; }
-                    else if (lo > a.chi2thr) { need_exact[k] = false; harm_ok[k] = false; }
-                }
-            }
-            any_exact |= need_exact[k];
-        }
-        if (any_exact) {
-            bool valid[PX]; double acc[PX];
-#pragma unroll
-            for (int k = 0; k < PX; ++k) { valid[k] = true; acc[k] = 0.0; }
+            for (int k = 0; k < PX; ++k) { S0d[k] = Sc[k] = Ss[k] = Sc4[k] = Ss4[k] = Sffd[k] = Id[k] = 0.0; }
+#pragma unroll 3
             for (int i = 0; i < N; ++i) {
                 double v[PX];
                 VecLoad<T, PX>::ld(base + (long long)i * P, v);
+                const double c2 = bs.c2[i], s2 = bs.s2[i];
 #pragma unroll
                 for (int k = 0; k < PX; ++k) {
                     double f = v[k];
-                    if (pre) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
-                    // numpy's fused SIMD complex multiply: Re(a2 conj(e2)) = fma(a2r, c, -(a2i * (-s)))
-                    double ft = a0[k] + fma(a2r[k], bs.c2[i], a2i[k] * bs.s2[i]);
-                    if constexpr (NH == 2) ft = ft + fma(a4r[k], bs.c4[i], a4i[k] * bs.s4[i]);
-                    valid[k] = valid[k] && (ft > 0.0) && pb_finite(ft);
-                    double d = f - ft;
-                    acc[k] = acc[k] + (d * d) / ft;
+                    if (pre) {
+                        if (sep_int) Id[k] = Id[k] + pb_max0(v[k] - a.dark);
+                        f = pb_max0(f - a.sub);
+                        if (a.do_sqrt) f = sqrt(f);
+                    }
+                    S0d[k] = S0d[k] + f;
+                    Sc[k] = Sc[k] + f * c2;
+                    Ss[k] = Ss[k] + f * s2;
+                    if constexpr (NH == 2) {
+                        Sc4[k] = Sc4[k] + f * bs.c4[i];
+                        Ss4[k] = Ss4[k] + f * bs.s4[i];
+                    }
+                    Sffd[k] = fma(f, f, Sffd[k]);   // screening only (not parity relevant)
+                }
+            }
+            if (!sep_int) {
+#pragma unroll
+                for (int k = 0; k < PX; ++k) Id[k] = S0d[k];
+            }
+        }
+        const bool f64 = a.flags & PB_FLAG_OUT_F64;
+        PixOut o[PX];
+        HarmPix hp[PX];
+        double Iv[PX];
+        bool any_need = false;
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
+            hp[k] = harm_stage_a<NH>(a, p0 + k, S0d[k], Sc[k], Ss[k], Sc4[k], Ss4[k], Sffd[k], Iv[k]);
+            any_need |= hp[k].need;
+        }
+        if (any_need) {
+            // rare path: the reference's fp64 fit/chi2 loop for the undecided pixels of this thread (stack re-read, L1/L2 hits)
+            ExactAcc ex[PX];
+#pragma unroll
+            for (int k = 0; k < PX; ++k) ex[k].init();
+            for (int i = 0; i < N; ++i) {
+                double v[PX];
+                VecLoad<T, PX>::ld(base + (long long)i * P, v);
+                double c4 = 0.0, s4 = 0.0;
+                if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    double f = v[k];
+                    if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
+                    ex[k].template step<NH>(hp[k], f, bs.c2[i], bs.s2[i], c4, s4);
                 }
             }
 #pragma unroll
             for (int k = 0; k < PX; ++k)
-                if (need_exact[k]) {
-                    double chi2 = acc[k] / dN;
-                    harm_ok[k] = valid[k] && (chi2 <= a.chi2thr) && (chi2 > 0.0);
-                }
+                if (hp[k].need) hp[k].m = ex[k].decide(a);
         }
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            const long long p = p0 + k;
-            if (p >= P) break;
-            const uint32_t bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
-            double I = a.intensity_in ? __ldg(a.intensity_in + p) : (sep_int ? Isum[k] : S0[k]);
-            bool m = a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, bits, I);
-            m = m && harm_ok[k];
-            const double inv = 1.0 / a0[k];
-            double A2 = a2r[k] * inv, B2 = a2i[k] * inv;
-            if (!(pb_finite(A2) && pb_finite(B2))) { A2 = pb_nan(); B2 = pb_nan(); }
-            double v0 = pb_nan(), v1 = pb_nan(), v2 = pb_nan(), v3 = pb_nan();
-            if (NH == 1) {
-                if (m) {
-                    lut_lookup(a, A2, B2, v0, v1);
-                    if (pb_finite(v0)) v0 = pb_pymod(v0 + a.rot_stick, 180.0);
-                    m = pb_finite(v0) && pb_finite(v1);
-                    // the reference keeps a finite rho next to a NaN psi (PP:3021-3024); both tables share their NaN rim
-                }
-            } else {
-                double A4 = a4r[k] * inv, B4 = a4i[k] * inv;
-                if (!(pb_finite(A4) && pb_finite(B4))) { A4 = pb_nan(); B4 = pb_nan(); }
-                if (m) {
-                    double r = (atan2(B2, A2) * RAD2DEG) / 2.0;
-                    r = pb_pymod(r + a.rot_stick, 180.0);
-                    double ab2 = hypot(A2, B2), ab4 = hypot(A4, B4);
-                    v0 = r;
-                    v1 = 1.5 * ab2;
-                    v2 = (6.0 * ab4) * cos(4.0 * (0.25 * atan2(B4, A4) - r * DEG2RAD));
-                    if (a.method == PB_SHG) v3 = (-0.5 * (ab4 - ab2)) / (ab4 + ab2) - 0.65;
-                }
-            }
-            store_any(out.var[0], p, v0, out64);
-            store_any(out.var[1], p, v1, out64);
+        for (int k = 0; k < PX; ++k) o[k] = harm_stage_b<NH>(a, hs, do_hist, hp[k]);
+        if constexpr (PX == 4) {
+            store4(out.var[0], p0, o[0].v0, o[1].v0, o[2].v0, o[3].v0, f64);
+            store4(out.var[1], p0, o[0].v1, o[1].v1, o[2].v1, o[3].v1, f64);
             if constexpr (NH == 2) {
-                store_any(out.var[2], p, v2, out64);
-                if (a.method == PB_SHG) store_any(out.var[3], p, v3, out64);
+                store4(out.var[2], p0, o[0].v2, o[1].v2, o[2].v2, o[3].v2, f64);
+                if (a.method == PB_SHG) store4(out.var[3], p0, o[0].v3, o[1].v3, o[2].v3, o[3].v3, f64);
             }
-            store_any(out.intmap, p, m ? a0[k] : pb_nan(), out64);
-            if (out.intensity && !a.intensity_in) reinterpret_cast<double *>(out.intensity)[p] = I;
-            if (out.mask) out.mask[p] = (uint8_t)m;
-            if (out.rho_angle) store_any(out.rho_angle, p, (v0 == v0) ? pb_pymod(v0 - a.ref_angle, 180.0) : pb_nan(), out64);
-            if (out.rho_contour && a.edge) {
-                double e = __ldg(a.edge + p);
-                store_any(out.rho_contour, p, (pb_finite(v0) && pb_finite(e)) ? pb_pymod(v0 - e, 180.0) : pb_nan(), out64);
+            store4(out.intmap, p0, o[0].a0m, o[1].a0m, o[2].a0m, o[3].a0m, f64);
+            if (out.mask) *reinterpret_cast<uchar4 *>(out.mask + p0) = make_uchar4(o[0].m, o[1].m, o[2].m, o[3].m);
+            if (out.intensity && !a.intensity_in) {
+                double2 *d = reinterpret_cast<double2 *>(reinterpret_cast<double *>(out.intensity) + p0);
+                d[0] = make_double2(Iv[0], Iv[1]); d[1] = make_double2(Iv[2], Iv[3]);
             }
-            if (do_hist && out.hist) {
-                hist_add(a, hs, 0, v0, bits);
-                hist_add(a, hs, 1, v1, bits);
-                if constexpr (NH == 2) {
-                    hist_add(a, hs, 2, v2, bits);
-                    if (a.method == PB_SHG) hist_add(a, hs, 3, v3, bits);
+            if (out.rho_angle || (out.rho_contour && a.edge)) {
+#pragma unroll
+                for (int k = 0; k < PX; ++k) {
+                    const long long p = p0 + k;
+                    if (out.rho_angle) store1(out.rho_angle, p, (o[k].v0 == o[k].v0) ? pb_pymod(o[k].v0 - a.ref_angle, 180.0) : pb_nan(), f64);
+                    if (out.rho_contour && a.edge) {
+                        const double e = __ldg(a.edge + p);
+                        store1(out.rho_contour, p, (pb_finite(o[k].v0) && pb_finite(e)) ? pb_pymod(o[k].v0 - e, 180.0) : pb_nan(), f64);
+                    }
                 }
             }
+        } else {
+            store_pixel<NH>(a, out, p0, o[0], Iv[0], f64);
         }
     }
-    if (do_hist && out.hist) hist_flush(a, hs, out.hist);
+    if (do_hist) hist_flush(a, hs, out.hist);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,11 +243,12 @@ __global__ void __launch_bounds__(256) k_pixel_harm(PixArgs a, typename BasisSel
 template <typename T>
 __global__ void __launch_bounds__(256) k_pixel_4polar(PixArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0;
-    HistSmem hs;
-    if (do_hist) hs = hist_setup(a, smem);
     const int stack = blockIdx.y;
     const pb_outputs out = a.outs[stack];
+    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
+    HistSmem hs;
+    hs.cnt = nullptr; hs.edges = nullptr;
+    if (do_hist) hs = hist_setup(a, smem);
     const long long P = a.P;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool out64 = a.flags & PB_FLAG_OUT_F64;
@@ -310,43 +296,50 @@ __global__ void __launch_bounds__(256) k_pixel_4polar(PixArgs a) {
         m = m && (lam < 1.0 / 3.0) && (lam > 0.0) && (three_d ? (pzz > lam) : true);
         double v0 = pb_nan(), v1 = pb_nan(), v2 = pb_nan();
         if (m) {
-            v0 = pb_pymod(0.5 * (atan2(puv, pxy) * RAD2DEG) + a.rot_stick, 180.0);
-            v1 = 2.0 * (acos((-1.0 + sqrt(9.0 - 24.0 * lam)) / 2.0) * RAD2DEG);
-            if (three_d) v2 = acos(sqrt((pzz - lam) / (1.0 - 3.0 * lam))) * RAD2DEG;
+            v0 = pb_pymod(0.5 * (atan2(puv, pxy) * PB_RAD2DEG) + a.rot_stick, 180.0);
+            v1 = 2.0 * (acos((-1.0 + sqrt(9.0 - 24.0 * lam)) / 2.0) * PB_RAD2DEG);
+            if (three_d) v2 = acos(sqrt((pzz - lam) / (1.0 - 3.0 * lam))) * PB_RAD2DEG;
         }
-        store_any(out.var[0], p, v0, out64);
-        store_any(out.var[1], p, v1, out64);
-        if (three_d) store_any(out.var[2], p, v2, out64);
-        store_any(out.intmap, p, m ? a0 : pb_nan(), out64);
+        store1(out.var[0], p, v0, out64);
+        store1(out.var[1], p, v1, out64);
+        if (three_d) store1(out.var[2], p, v2, out64);
+        store1(out.intmap, p, m ? a0 : pb_nan(), out64);
         if (out.intensity && !a.intensity_in) reinterpret_cast<double *>(out.intensity)[p] = I;
         if (out.mask) out.mask[p] = (uint8_t)m;
-        if (out.rho_angle) store_any(out.rho_angle, p, (v0 == v0) ? pb_pymod(v0 - a.ref_angle, 180.0) : pb_nan(), out64);
+        if (out.rho_angle) store1(out.rho_angle, p, (v0 == v0) ? pb_pymod(v0 - a.ref_angle, 180.0) : pb_nan(), out64);
         if (out.rho_contour && a.edge) {
             double e = __ldg(a.edge + p);
-            store_any(out.rho_contour, p, (pb_finite(v0) && pb_finite(e)) ? pb_pymod(v0 - e, 180.0) : pb_nan(), out64);
+            store1(out.rho_contour, p, (pb_finite(v0) && pb_finite(e)) ? pb_pymod(v0 - e, 180.0) : pb_nan(), out64);
         }
-        if (do_hist && out.hist) {
+        if (do_hist && m) {
             hist_add(a, hs, 0, v0, bits);
             hist_add(a, hs, 1, v1, bits);
-            if (three_d) hist_add(a, hs, 2, v2, bits);
+            if (three_d && pb_finite(v2)) hist_add(a, hs, 2, v2, bits);
         }
     }
-    if (do_hist && out.hist) hist_flush(a, hs, out.hist);
+    if (do_hist) hist_flush(a, hs, out.hist);
 }
 
 template <typename T, int NH>
 cudaError_t launch_harm_t(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, size_t smem, cudaStream_t st) {
-    const int threads = 256;
+    const int threads = 128;
     // PX = 4 needs every plane (and every stack) to start on a 4-element boundary
-    bool vec = (a.P % 4 == 0) && (a.stack_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.stack) % (4 * sizeof(T))) == 0);
-    if (vec) {
-        long long nthr = a.P / 4;
-        dim3 grid((unsigned)((nthr + threads - 1) / threads), n_stacks);
-        k_pixel_harm<T, NH, 4><<<grid, threads, smem, st>>>(a, bs);
-    } else {
-        dim3 grid((unsigned)((a.P + threads - 1) / threads), n_stacks);
-        k_pixel_harm<T, NH, 1><<<grid, threads, smem, st>>>(a, bs);
+    const bool vec = (a.P % 4 == 0) && (a.stack_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.stack) % (4 * sizeof(T))) == 0);
+    // integer fast path: integer stack, integer-valued offsets that fit the element range, no sqrt
+    constexpr bool is_int = std::is_same<T, uint8_t>::value || std::is_same<T, uint16_t>::value;
+    const bool fast = is_int && !a.from_field && !a.do_sqrt && !a.intensity_in && a.sub == floor(a.sub) && a.dark == floor(a.dark) &&
+                      a.sub >= 0 && a.sub <= 65536.0 && a.dark >= 0 && a.dark <= 65536.0;
+    const long long nthr = vec ? a.P / 4 : a.P;
+    dim3 grid((unsigned)((nthr + threads - 1) / threads), n_stacks);
+    if constexpr (is_int) {
+        if (fast) {
+            if (vec) k_pixel_harm<T, NH, 4, 1><<<grid, threads, smem, st>>>(a, bs);
+            else k_pixel_harm<T, NH, 1, 1><<<grid, threads, smem, st>>>(a, bs);
+            return cudaGetLastError();
+        }
     }
+    if (vec) k_pixel_harm<T, NH, 4, 0><<<grid, threads, smem, st>>>(a, bs);
+    else k_pixel_harm<T, NH, 1, 0><<<grid, threads, smem, st>>>(a, bs);
     return cudaGetLastError();
 }
 
@@ -360,7 +353,7 @@ cudaError_t pb_launch_pixel_harm(const PixArgs &a, const Basis2 &bs, int dtype, 
     size_t smem = pb_hist_smem_bytes(a.n_vars, a.nbins, a.n_groups);
     const bool one = a.method == PB_1PF;
     Basis1 b1;
-    if (one) { memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2)); }
+    if (one) { memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2)); memcpy(b1.kc2, bs.kc2, sizeof(b1.kc2)); memcpy(b1.ks2, bs.ks2, sizeof(b1.ks2)); }
 #define PB_DISPATCH(T)                                                                     \
     return one ? launch_harm_t<T, 1>(a, b1, n_stacks, smem, st) : launch_harm_t<T, 2>(a, bs, n_stacks, smem, st)
     switch (dtype) {

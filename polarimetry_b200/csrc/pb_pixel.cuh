@@ -1,0 +1,252 @@
+// pb_pixel.cuh -- per-pixel device code shared by the fused per-pixel kernel (pb_pixel.cu) and the fused
+// row-march kernel (pb_march.cu): shared-memory histograms, threshold/ROI test, disk-cone LUT inversion,
+// certified fit/chi2 screening and the per-pixel epilogue of the harmonic modalities.
+// Arithmetic order of everything that reaches a mask, a LUT coordinate or a bin follows oracle/contract.c.
+#pragma once
+#include "pb_dev.cuh"
+
+struct HistSmem {
+    unsigned *cnt;     // [n_groups][n_vars][nbins]
+    double *edges;     // [n_vars][nbins+1]
+};
+
+__device__ __forceinline__ HistSmem hist_setup(const PixArgs &a, unsigned char *smem) {
+    HistSmem h;
+    const int ne = a.n_vars * (a.nbins + 1);
+    h.edges = reinterpret_cast<double *>(smem);
+    h.cnt = reinterpret_cast<unsigned *>(smem + sizeof(double) * ne);
+    const int nc = a.n_groups * a.n_vars * a.nbins;
+    for (int k = threadIdx.x; k < ne; k += blockDim.x) h.edges[k] = a.hist_edges[k];
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) h.cnt[k] = 0u;
+    __syncthreads();
+    return h;
+}
+
+__device__ __forceinline__ void hist_flush(const PixArgs &a, const HistSmem &h, int64_t *dst) {
+    __syncthreads();
+    const int nc = a.n_groups * a.n_vars * a.nbins;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+        const unsigned c = h.cnt[k];
+        if (c) atomicAdd(reinterpret_cast<unsigned long long *>(dst) + k, (unsigned long long)c);
+    }
+}
+
+// np.histogram rule on explicit edges: [e_k, e_{k+1}), last bin closed, outside dropped. `val` must be finite.
+__device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, int var, double val, uint32_t bits) {
+    double d = val;
+    if ((a.hist_is_rho >> var) & 1u) {
+        // Variable.histo re-wrap d = mod(2(d + rot), 360)/2 (PC:341-342); for rot == 0 and 0 <= d <= 180 it is d, except 180 -> 0
+        if (a.rot_fig == 0.0 && d >= 0.0 && d <= 180.0) d = (d == 180.0) ? 0.0 : d;
+        else d = pb_pymod(2.0 * (d + a.rot_fig), 360.0) / 2.0;
+    }
+    const double *e = h.edges + var * (a.nbins + 1);
+    const int nb = a.nbins;
+    if (!(d >= e[0]) || !(d <= e[nb])) return;
+    int k = (int)((d - e[0]) * a.inv_bin_width[var]);
+    k = max(0, min(k, nb - 1));
+    if (d < e[k]) { do { --k; } while (k > 0 && d < e[k]); }
+    else { while (k < nb - 1 && d >= e[k + 1]) ++k; }
+    unsigned *c = h.cnt + var * nb + k;
+    if (a.n_groups == 1) {
+        if (bits & a.group_bits[0]) atomicAdd(c, 1u);
+    } else {
+        for (int g = 0; g < a.n_groups; ++g)
+            if (bits & a.group_bits[g]) atomicAdd(c + g * a.n_vars * nb, 1u);
+    }
+}
+
+// threshold / ROI test, PP:2891 + PP:2967: any_r( bit_r & I >= ILow_r )
+__device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double I) {
+    if (a.n_rois == 0) return (bits != 0u) && (I >= a.roi_ilow[0]);
+    bool ok = false;
+    for (int r = 0; r < a.n_rois; ++r) ok |= ((bits >> r) & 1u) && (I >= a.roi_ilow[r]);
+    return ok;
+}
+
+// disk-cone LUT cell and normalised distance along one axis: g[i] <= x < g[i+1], last cell closed
+// (scipy RegularGridInterpolator rule); t = (x - g[i]) / (g[i+1] - g[i]). Caller guarantees g[0] <= x <= g[n-1].
+__device__ __forceinline__ int lut_axis(const double *g, int n, double half_nm1, double x, double &t) {
+    int k = __double2int_rd(fma(x, half_nm1, half_nm1));       // ~ (x+1)(n-1)/2: off by at most one cell
+    k = max(0, min(k, n - 2));
+    double ga = __ldg(g + k), gb = __ldg(g + k + 1);
+    if (x < ga) {
+        do { --k; gb = ga; ga = __ldg(g + k); } while (k > 0 && x < ga);
+    } else if (x >= gb && k < n - 2) {
+        do { ++k; ga = gb; gb = __ldg(g + k + 1); } while (k < n - 2 && x >= gb);
+    }
+    t = (x - ga) / (gb - ga);
+    return k;
+}
+
+// bilinear interpolation of the interleaved (rho, psi) table in the reference's evaluation order
+// (SURVEY 8a row a6): v = 0 + V00 w00 + V01 w01 + V10 w10 + V11 w11, w = ((1)(1-t0))(1-t1) ... ; NaN corners propagate.
+__device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y, double &rho, double &psi) {
+    rho = pb_nan(); psi = pb_nan();
+    const double *g = a.grid;
+    const int n = a.lut_n;
+    const double g0 = __ldg(g), g1 = __ldg(g + n - 1);
+    if (!(x >= g0 && x <= g1 && y >= g0 && y <= g1)) return;   // out of range or NaN -> fill value NaN
+    const double half_nm1 = 0.5 * (double)(n - 1);
+    double t0, t1;
+    const int i0 = lut_axis(g, n, half_nm1, x, t0), i1 = lut_axis(g, n, half_nm1, y, t1);
+    const double u0 = 1.0 - t0, u1 = 1.0 - t1;
+    const double w00 = u0 * u1, w01 = u0 * t1, w10 = t0 * u1, w11 = t0 * t1;    // (1.0 * u0) == u0 exactly
+    const double2 *T = a.lut + (long long)i0 * n + i1;
+    const double2 v00 = __ldg(T), v01 = __ldg(T + 1), v10 = __ldg(T + n), v11 = __ldg(T + n + 1);
+    double r = 0.0 + v00.x * w00, q = 0.0 + v00.y * w00;
+    r = r + v01.x * w01; q = q + v01.y * w01;
+    r = r + v10.x * w10; q = q + v10.y * w10;
+    r = r + v11.x * w11; q = q + v11.y * w11;
+    rho = r; psi = q;
+}
+
+constexpr double PB_RAD2DEG = 180.0 / 3.141592653589793238462643383279502884;
+constexpr double PB_DEG2RAD = 3.141592653589793238462643383279502884 / 180.0;
+
+struct PixOut {
+    double v0, v1, v2, v3, a0m;
+    bool m;
+};
+
+// state of one pixel between the two stages of the epilogue
+struct HarmPix {
+    double a0, a2r, a2i, a4r, a4i;
+    uint32_t bits;
+    bool m;       // still a candidate (threshold / ROI passed, a0 != 0, screening did not reject)
+    bool need;    // the fit/chi2 decision needs the reference's fp64 loop (ExactAcc)
+};
+
+// accumulator of the reference's fit/chi2 loop for one pixel (PP:2990-3000)
+struct ExactAcc {
+    double acc;
+    bool valid;
+    __device__ __forceinline__ void init() { acc = 0.0; valid = true; }
+    // ft = a0 + Re(a2 conj(e2_i)) [+ Re(a4 conj(e4_i))], numpy's fused SIMD complex multiply: fma(a2r, c, -(a2i * (-s)))
+    template <int NH>
+    __device__ __forceinline__ void step(const HarmPix &h, double f, double c2, double s2, double c4, double s4) {
+        double ft = h.a0 + fma(h.a2r, c2, h.a2i * s2);
+        if constexpr (NH == 2) ft = ft + fma(h.a4r, c4, h.a4i * s4);
+        valid = valid && (ft > 0.0) && pb_finite(ft);
+        const double d = f - ft;
+        acc = acc + (d * d) / ft;
+    }
+    __device__ __forceinline__ bool decide(const PixArgs &a) const {
+        const double chi2 = acc / a.dN;
+        return valid && (chi2 <= a.chi2thr) && (chi2 > 0.0);
+    }
+};
+
+// Stage A (PP:2987-3000 decisions): threshold / ROI test, a0 / a2 / a4, certified screening of
+// (all fit_i > 0) & (chi2 <= thr) & (chi2 > 0).
+//   S0,Sc,Ss,(Sc4,Ss4): the sequential sums of PP:2987-2994 ; Sff: sum f^2 (screening only) ; I: threshold image value
+template <int NH>
+__device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, double S0, double Sc, double Ss, double Sc4, double Ss4,
+                                                double Sff, double I) {
+    HarmPix h;
+    h.a0 = pb_nan(); h.a2r = h.a2i = h.a4r = h.a4i = 0.0;
+    h.need = false;
+    h.bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
+    h.m = a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, h.bits, I);
+    if (!h.m) return h;
+    // S0 / N correctly rounded without a division: fma(S0, rhi, S0*rlo) with (rhi, rlo) the double-double 1/N
+    // (tests/test_shortcuts.py; x/N is never within 2^-60 of a rounding boundary, the approximation error is 2^-105)
+    const double a0 = fma(S0, a.invN_hi, S0 * a.invN_lo);
+    if (a0 == 0.0) { h.m = false; return h; }                  // a0 -> NaN (PP:2988): fit is NaN, pixel invalid
+    h.a0 = a0;
+    h.a2r = a.k2 * Sc; h.a2i = a.k2 * Ss;
+    if constexpr (NH == 2) { h.a4r = a.k2 * Sc4; h.a4i = a.k2 * Ss4; }
+    // From the orthogonality identity
+    //   sum_i (f_i - fit_i)^2 = sum f^2 - N (a0^2 + |a2|^2/2 + |a4|^2/2),  a0 - |a2| - |a4| <= fit_i <= a0 + |a2| + |a4|
+    // evaluated in fp64 up to the cancellation, then in fp32 with explicit margins covering every rounding.
+    h.need = true;
+    if (!(a.flags & PB_FLAG_EXACT_CHI2)) {
+        const double q2 = fma(h.a2r, h.a2r, h.a2i * h.a2i);
+        double qq = q2;
+        const float q2f = (float)q2;
+        float ampf = q2f > 0.0f ? q2f * rsqrtf(q2f) : 0.0f;
+        if constexpr (NH == 2) {
+            const double q4 = fma(h.a4r, h.a4r, h.a4i * h.a4i);
+            qq = q2 + q4;
+            const float q4f = (float)q4;
+            ampf += q4f > 0.0f ? q4f * rsqrtf(q4f) : 0.0f;
+        }
+        const double model = a.dN * fma(0.5, qq, a0 * a0);
+        const float ssef = (float)(Sff - model), a0f = (float)a0, Sf = (float)Sff;
+        const float errf = fmaf(4e-12f, Sf, 1e-6f * fabsf(ssef));
+        const float fmn = fmaf(a0f, 1.0f - 2e-6f, -ampf * (1.0f + 1e-5f));
+        const float fmx = fmaf(a0f, 1.0f + 2e-6f, ampf * (1.0f + 1e-5f));
+        const float lo = ssef - errf, hi = ssef + errf;
+        if (fmn > 1e-6f * a0f && fmx < 1e30f && Sf < 1e30f) {
+            if (lo > 0.0f && hi * (1.0f + 1e-5f) <= a.thr_lo_n * fmn) h.need = false;                 // certainly passes
+            else if (lo * (1.0f - 1e-5f) > a.thr_hi_n * fmx) { h.need = false; h.m = false; }         // certainly fails
+        }
+    }
+    return h;
+}
+
+// Stage B (PP:3017-3040 outputs, PP:3052, histograms) for a pixel whose fit/chi2 decision is h.m.
+template <int NH>
+__device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem &hs, bool do_hist, const HarmPix &h) {
+    PixOut o;
+    o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
+    o.m = false;
+    if (!h.m) return o;
+    const double inv = 1.0 / h.a0;
+    double A2 = h.a2r * inv, B2 = h.a2i * inv;
+    double v0, v1;
+    bool m = true;
+    if constexpr (NH == 1) {
+        // a non-finite A2/B2 is NaN'ed by divide_ext (PC:58-62) and then falls out of the LUT range: same result here
+        lut_lookup(a, A2, B2, v0, v1);
+        if (pb_finite(v0)) v0 = pb_pymod(v0 + a.rot_stick, 180.0);
+        // the reference keeps a finite rho next to a NaN psi (PP:3021-3024); the mask needs both finite
+        m = pb_finite(v0) && pb_finite(v1);
+        o.v0 = v0; o.v1 = v1;
+    } else {
+        double A4 = h.a4r * inv, B4 = h.a4i * inv;
+        if (!(pb_finite(A2) && pb_finite(B2))) { A2 = pb_nan(); B2 = pb_nan(); }
+        if (!(pb_finite(A4) && pb_finite(B4))) { A4 = pb_nan(); B4 = pb_nan(); }
+        double r = (atan2(B2, A2) * PB_RAD2DEG) / 2.0;
+        r = pb_pymod(r + a.rot_stick, 180.0);
+        const double ab2 = hypot(A2, B2), ab4 = hypot(A4, B4);
+        o.v0 = v0 = r;
+        o.v1 = v1 = 1.5 * ab2;
+        o.v2 = (6.0 * ab4) * cos(4.0 * (0.25 * atan2(B4, A4) - r * PB_DEG2RAD));
+        if (a.method == PB_SHG) o.v3 = (-0.5 * (ab4 - ab2)) / (ab4 + ab2) - 0.65;
+    }
+    o.m = m;
+    if (m) o.a0m = h.a0;
+    if (do_hist) {
+        if (pb_finite(v0)) hist_add(a, hs, 0, v0, h.bits);
+        if (pb_finite(v1)) hist_add(a, hs, 1, v1, h.bits);
+        if constexpr (NH == 2) {
+            if (pb_finite(o.v2)) hist_add(a, hs, 2, o.v2, h.bits);
+            if (a.method == PB_SHG && pb_finite(o.v3)) hist_add(a, hs, 3, o.v3, h.bits);
+        }
+    }
+    return o;
+}
+
+// scalar stores of one pixel's results (float or double maps)
+__device__ __forceinline__ void store1(void *base, long long p, double v, bool f64) {
+    if (!base) return;
+    if (f64) reinterpret_cast<double *>(base)[p] = v; else reinterpret_cast<float *>(base)[p] = (float)v;
+}
+
+template <int NH>
+__device__ __forceinline__ void store_pixel(const PixArgs &a, const pb_outputs &out, long long p, const PixOut &o, double I, bool f64) {
+    store1(out.var[0], p, o.v0, f64);
+    store1(out.var[1], p, o.v1, f64);
+    if constexpr (NH == 2) {
+        store1(out.var[2], p, o.v2, f64);
+        if (a.method == PB_SHG) store1(out.var[3], p, o.v3, f64);
+    }
+    store1(out.intmap, p, o.a0m, f64);
+    if (out.mask) out.mask[p] = (uint8_t)o.m;
+    if (out.intensity && !a.intensity_in) reinterpret_cast<double *>(out.intensity)[p] = I;
+    if (out.rho_angle) store1(out.rho_angle, p, (o.v0 == o.v0) ? pb_pymod(o.v0 - a.ref_angle, 180.0) : pb_nan(), f64);
+    if (out.rho_contour && a.edge) {
+        const double e = __ldg(a.edge + p);
+        store1(out.rho_contour, p, (pb_finite(o.v0) && pb_finite(e)) ? pb_pymod(o.v0 - e, 180.0) : pb_nan(), f64);
+    }
+}

@@ -150,7 +150,7 @@ cudaError_t pb_launch_fit_maps(const double *f, const uint8_t *mask, long long P
     unsigned blocks = (unsigned)((P + 255) / 256);
     if (nharm == 1) {
         Basis1 b1;
-        memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));
+        memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2)); memset(b1.kc2, 0, sizeof(b1.kc2)); memset(b1.ks2, 0, sizeof(b1.ks2));
         k_fit_maps<1><<<blocks, 256, 0, st>>>(f, mask, P, N, b1, fit, chi2);
     } else {
         k_fit_maps<2><<<blocks, 256, 0, st>>>(f, mask, P, N, bs, fit, chi2);
