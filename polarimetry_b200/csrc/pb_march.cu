@@ -28,143 +28,203 @@ void pb_ddrecip(int n, double *hi, double *lo);   // pb_api.cu
 
 namespace {
 
-constexpr int MR = 32;   // rows per CTA (= lanes of a chain warp)
-constexpr int PL = 2;    // planes (lines) per chain thread
+constexpr int MR = 32;     // rows per CTA (= lanes of a chain warp)
+constexpr int PL = 2;      // planes (lines) per chain thread
+constexpr int QMAX = 6;    // tile positions per loader thread
 
 struct MarchArgs {
     int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
     int steps;                   // number of XT-wide steps over the extended row (W + bw - 1)
     int tile_rows;               // MR + bh - 1
-    int rp;                      // raw tile row pitch in uint16 (2 * odd)
-    int groups;                  // loader groups splitting the angle loop
-    int npos;                    // tile_rows * XT loader positions
+    int cw, lw;                  // compute (chain + pixel) warps, loader warps
+    int isub, idark;             // dark + removed_intensity, dark (integers on this path)
     double bh_hi, bh_lo, bw_hi, bw_lo;   // double-double reciprocals of the bin sizes
-    unsigned off_T, off_f;       // byte offsets of the T partials and of fbuf in dynamic shared memory (after the histogram area)
-    unsigned off_raw;
+    unsigned off_raw, off_T, off_f;      // byte offsets in dynamic shared memory (after the histogram area)
+    unsigned raw_bytes, T_bytes;         // size of ONE buffer of the double-buffered raw / T tiles
 };
 
 template <int BW> struct StepWidth { static constexpr int M = (8 + BW - 1) / BW; static constexpr int XT = BW * M; };
 template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr int XT = 8; };
 
-template <typename UT, int NH, int BW>
-__global__ void __launch_bounds__(512, 2) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
+// SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
+template <typename UT, int NH, int BW, bool SQ>
+__global__ void __maxnreg__(80) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
-    constexpr int MAXLD = 24;                           // register budget for the prefetched raw values per thread
+    constexpr int RW = ((XT + 1) / 2) | 1;              // raw tile row pitch in 32-bit words (odd: conflict-free chain loads)
+    constexpr int RP = 2 * RW;                          // ... in uint16
     extern __shared__ __align__(16) unsigned char smem[];
     const pb_outputs out = a.outs[blockIdx.y];
     const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
     HistSmem hs;
     hs.cnt = nullptr; hs.edges = nullptr;
     if (do_hist) hs = hist_setup(a, smem);
-    uint16_t *raw = reinterpret_cast<uint16_t *>(smem + ma.off_raw);      // [N][tile_rows][rp] clamped (v - sub)
-    int *Tp = reinterpret_cast<int *>(smem + ma.off_T);                   // [groups][tile_rows][XT] partial sums of clamp(v - dark)
-    double *fbuf = reinterpret_cast<double *>(smem + ma.off_f);           // [N+1][MR][FP]
 
     const int N = a.N, H = a.H, W = a.W;
-    const long long P = a.P;
-    const UT *stack = reinterpret_cast<const UT *>(a.stack) + (long long)blockIdx.y * a.stack_stride;
     const int y0 = blockIdx.x * MR;
-    const int tid = threadIdx.x, lane = tid & 31, plane0 = (tid >> 5) * PL;   // chains (plane0 .. plane0+PL-1, row y0 + lane)
-    const int isub = (int)a.sub, idark = (int)a.dark;
-    const bool sep = isub != idark;
-    const int bh = ma.bh, TR = ma.tile_rows, RP = ma.rp, G = ma.groups, NPOS = ma.npos;
-    const int plane_pitch = TR * RP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bh = SQ ? BW : ma.bh;
+    const int TR = SQ ? MR + BW - 1 : ma.tile_rows;
+    const int NPOS = TR * XT;
+    const int plane_pitch = TR * RP;                     // uint16 per plane of the raw tile
+    const int steps = ma.steps;
 
-    // loader role: position (r', j) of the tile, angles i = g, g + G, ...
-    const int lpos = tid % NPOS, lg = tid / NPOS;
-    const bool ldr = lg < G;
-    const int lr = lpos / XT, lj = lpos - lr * XT;
-    const long long lrow_off = (long long)pb_reflect(y0 - ma.hh + lr, H) * W;
-    unsigned ldv[MAXLD];
-
-    auto prefetch = [&](int t) {
-        if (!ldr) return;
-        const int col = pb_reflect(t * XT + lj - ma.hw, W);
-        const UT *src = stack + lrow_off + col;
+    if (warp >= ma.cw) {
+        // =========================== loader warps ===========================
+        // raw stack -> shared memory, dark-subtracted and clamped (PP:2953), for step t+1 while the compute warps work on step t;
+        // also the per-position total-intensity sums sum_i max(v - dark, 0) (PC:261) for the threshold image.
+        const UT *stack = reinterpret_cast<const UT *>(a.stack) + (long long)blockIdx.y * a.stack_stride;
+        const int ltid = tid - ma.cw * 32, LT = ma.lw * 32;
+        const int isub = ma.isub, idark = ma.idark;
+        const bool sep = isub != idark;
+        const unsigned uP = (unsigned)a.P;
+        unsigned rowoff[QMAX];
+        int jj[QMAX], soff[QMAX];
 #pragma unroll
-        for (int u = 0; u < MAXLD; ++u) {
-            const int i = lg + u * G;
-            if (i < N) ldv[u] = (unsigned)__ldg(src + (long long)i * P);
+        for (int q = 0; q < QMAX; ++q) {
+            const int pos = ltid + q * LT;
+            const int r = pos / XT;
+            jj[q] = pos - r * XT;
+            soff[q] = r * RP + jj[q];
+            rowoff[q] = pos < NPOS ? (unsigned)pb_reflect(y0 - ma.hh + r, H) * (unsigned)W : 0u;
+            if (pos >= NPOS) jj[q] = -1;
         }
-    };
-    auto commit = [&]() {
-        if (!ldr) return;
-        int tsum = 0;
-        uint16_t *dst = raw + lr * RP + lj;
+        for (int t = 0; t <= steps; ++t) {
+            // fill buffer t&1 with the data of step t (t == steps: nothing left, just take part in the barriers)
+            if (t < steps) {
+                uint16_t *rawb = reinterpret_cast<uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
+                int *Tb = reinterpret_cast<int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
+                unsigned off[QMAX];
+                int tsum[QMAX];
 #pragma unroll
-        for (int u = 0; u < MAXLD; ++u) {
-            const int i = lg + u * G;
-            if (i < N) {
-                const int v = (int)ldv[u];
-                const int f = max(v - isub, 0);
-                dst[i * plane_pitch] = (uint16_t)f;
-                tsum += sep ? max(v - idark, 0) : f;
-            }
-        }
-        Tp[lg * NPOS + lpos] = tsum;
-    };
-
-    // chain state
-    double tmp[PL], ring[PL][BW];
+                for (int q = 0; q < QMAX; ++q) {
+                    off[q] = rowoff[q] + (unsigned)(jj[q] >= 0 ? pb_reflect(t * XT + jj[q] - ma.hw, W) : 0);
+                    tsum[q] = 0;
+                }
+                unsigned ip = 0;
+                uint16_t *dst = rawb;
+                int i = 0;
+                for (; i + 2 <= N; i += 2) {
+                    unsigned v0[QMAX], v1[QMAX];
 #pragma unroll
-    for (int c = 0; c < PL; ++c) {
-        tmp[c] = 0.0;
+                    for (int q = 0; q < QMAX; ++q) {
+                        v0[q] = (unsigned)__ldg(stack + (off[q] + ip));
+                        v1[q] = (unsigned)__ldg(stack + (off[q] + ip + uP));
+                    }
 #pragma unroll
-        for (int s = 0; s < BW; ++s) ring[c][s] = 0.0;
-    }
-
-    prefetch(0);
-    for (int t = 0; t < ma.steps; ++t) {
-        commit();
-        __syncthreads();
-        if (t + 1 < ma.steps) prefetch(t + 1);
-        // ---- phase A: the (plane, row) lines advance XT extended positions
+                    for (int q = 0; q < QMAX; ++q) {
+                        if (jj[q] >= 0) {
+                            const int f0 = max((int)v0[q] - isub, 0), f1 = max((int)v1[q] - isub, 0);
+                            dst[soff[q]] = (uint16_t)f0;
+                            dst[soff[q] + plane_pitch] = (uint16_t)f1;
+                            tsum[q] += sep ? max((int)v0[q] - idark, 0) + max((int)v1[q] - idark, 0) : f0 + f1;
+                        }
+                    }
+                    ip += 2 * uP;
+                    dst += 2 * plane_pitch;
+                }
+                if (i < N) {
 #pragma unroll
-        for (int c = 0; c < PL; ++c) {
-            const int plane = plane0 + c;
-            if (plane > N) continue;
-            const bool is_int_plane = plane == N;
-            double *fo = fbuf + (plane * MR + lane) * FP;
-            const int e0 = t * XT;
-#pragma unroll
-            for (int j = 0; j < XT; ++j) {
-                int S1 = 0;
-                if (!is_int_plane) {
-                    const uint16_t *rp = raw + plane * plane_pitch + lane * RP + j;
-                    for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP];
-                } else {
-                    for (int g = 0; g < G; ++g) {
-                        const int *tp = Tp + g * NPOS + lane * XT + j;
-                        for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT];
+                    for (int q = 0; q < QMAX; ++q) {
+                        if (jj[q] >= 0) {
+                            const int v = (int)__ldg(stack + (off[q] + ip));
+                            const int f = max(v - isub, 0);
+                            dst[soff[q]] = (uint16_t)f;
+                            tsum[q] += sep ? max(v - idark, 0) : f;
+                        }
                     }
                 }
-                // (double)S1 exactly: (2^52 + S1) - 2^52 ; then RN(S1 / bh) unless the H pass is skipped (bh <= 1, PP:2944)
-                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-                const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-                double f;
-                if constexpr (BW == 1) {
-                    f = q;                                   // W pass skipped (size <= 1)
-                } else {
-                    const int e = e0 + j;
-                    const double old = ring[c][j % BW];
-                    ring[c][j % BW] = q;
-                    tmp[c] = (e < BW) ? tmp[c] + q : tmp[c] + (q - old);
-                    f = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);   // RN(tmp / bw)
-                }
-                fo[j] = f;
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q)
+                    if (jj[q] >= 0) Tb[ltid + q * LT] = tsum[q];
             }
+            __syncthreads();                 // (1) buffer t&1 complete (and, for t >= 1, phase B of step t-1 done)
+            if (t < steps) __syncthreads();  // (2) phase A of step t done
         }
-        __syncthreads();
-        // ---- phase B: the pixels completed by this step
-        if (tid < MR * XT) {
-            const int r = tid / XT, j = tid - r * XT;
-            const int k = t * XT + j - (BW - 1), y = y0 + r;
-            if (k >= 0 && k < W && y < H) {
-                const double *fp = fbuf + r * FP + j;
+    } else {
+        // =========================== compute warps ===========================
+        double *fbuf = reinterpret_cast<double *>(smem + ma.off_f);           // [N+1][MR][FP]
+        const int plane0 = warp * PL;                                          // chains (plane0 .. plane0+PL-1, row y0 + lane)
+        // chain state: running sum and the last BW first-pass outputs. The ring starts at 0.0 so that the first BW steps
+        // compute tmp + (q - 0.0) = tmp + q, i.e. scipy's left-to-right initial window sum, with the same instruction.
+        double tmp[PL], ring[PL][BW];
+#pragma unroll
+        for (int c = 0; c < PL; ++c) {
+            tmp[c] = 0.0;
+#pragma unroll
+            for (int s = 0; s < BW; ++s) ring[c][s] = 0.0;
+        }
+        double *const cfo = fbuf + (plane0 * MR + lane) * FP;
+        const int pr = tid / XT, pj = tid - pr * XT;                           // pixel role
+        const bool pix = tid < MR * XT && (y0 + pr) < H;
+        const double *const pfp = fbuf + pr * FP + pj;
+        const bool f64 = a.flags & PB_FLAG_OUT_F64;
+        __syncthreads();                      // (1) of t = 0
+        for (int t = 0; t < steps; ++t) {
+            const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
+            const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
+            // ---- phase A: the (plane, row) lines advance XT extended positions
+#pragma unroll
+            for (int c = 0; c < PL; ++c) {
+                const int plane = plane0 + c;
+                double *fo = cfo + c * (MR * FP);
+                if (plane < N) {
+                    const uint16_t *rp = rawb + plane * plane_pitch + lane * RP;
+#pragma unroll
+                    for (int j = 0; j < XT; ++j) {
+                        int S1 = 0;
+                        if constexpr (SQ) {
+#pragma unroll
+                            for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[dy * RP + j];
+                        } else {
+                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP + j];
+                        }
+                        // (double)S1 exactly: (2^52 + S1) - 2^52 ; then RN(S1 / bh) unless the H pass is skipped (bh <= 1, PP:2944)
+                        const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+                        const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+                        double f;
+                        if constexpr (BW == 1) {
+                            f = q;                                   // W pass skipped (size <= 1)
+                        } else {
+                            const double old = ring[c][j % BW];
+                            ring[c][j % BW] = q;
+                            tmp[c] = tmp[c] + (q - old);
+                            f = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);   // RN(tmp / bw)
+                        }
+                        fo[j] = f;
+                    }
+                } else if (plane == N) {
+                    // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
+                    const int *tp = Tb + lane * XT;
+#pragma unroll
+                    for (int j = 0; j < XT; ++j) {
+                        int S1 = 0;
+                        for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT + j];
+                        const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+                        const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+                        double f;
+                        if constexpr (BW == 1) {
+                            f = q;
+                        } else {
+                            const double old = ring[c][j % BW];
+                            ring[c][j % BW] = q;
+                            tmp[c] = tmp[c] + (q - old);
+                            f = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+                        }
+                        fo[j] = f;
+                    }
+                }
+            }
+            __syncthreads();                  // (2) fbuf of step t complete
+            // ---- phase B: the pixels completed by this step
+            const int k = t * XT + pj - (BW - 1);
+            if (pix && k >= 0 && k < W) {
                 double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
+                const double *fp = pfp;
+#pragma unroll 6
                 for (int i = 0; i < N; ++i) {
-                    const double f = fp[i * (MR * FP)];
+                    const double f = *fp;
+                    fp += MR * FP;
                     S0 = S0 + f;
                     Sc = Sc + f * bs.c2[i];
                     Ss = Ss + f * bs.s2[i];
@@ -172,10 +232,10 @@ __global__ void __launch_bounds__(512, 2) k_march(PixArgs a, typename BasisSel<N
                         Sc4 = Sc4 + f * bs.c4[i];
                         Ss4 = Ss4 + f * bs.s4[i];
                     }
-                    Sff = fma(f, f, Sff);                    // screening only
+                    Sff = fma(f, f, Sff);                        // screening only
                 }
-                const double I = fp[N * (MR * FP)];
-                const long long p = (long long)y * W + k;
+                const double I = *fp;                            // plane N: the binned total intensity
+                const long long p = (long long)(y0 + pr) * W + k;
                 HarmPix hp = harm_stage_a<NH>(a, p, S0, Sc, Ss, Sc4, Ss4, Sff, I);
                 if (hp.need) {
                     ExactAcc ex;
@@ -183,15 +243,15 @@ __global__ void __launch_bounds__(512, 2) k_march(PixArgs a, typename BasisSel<N
                     for (int i = 0; i < N; ++i) {
                         double c4 = 0.0, s4 = 0.0;
                         if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-                        ex.template step<NH>(hp, fp[i * (MR * FP)], bs.c2[i], bs.s2[i], c4, s4);
+                        ex.template step<NH>(hp, pfp[i * (MR * FP)], bs.c2[i], bs.s2[i], c4, s4);
                     }
                     hp.m = ex.decide(a);
                 }
                 const PixOut o = harm_stage_b<NH>(a, hs, do_hist, hp);
-                store_pixel<NH>(a, out, p, o, I, a.flags & PB_FLAG_OUT_F64);
+                store_pixel<NH>(a, out, p, o, I, f64);
             }
+            __syncthreads();                  // (1) of step t+1: fbuf free again, next tile in place
         }
-        __syncthreads();
     }
     if (do_hist) hist_flush(a, hs, out.hist);
 }
@@ -205,32 +265,40 @@ template <typename UT, int NH, int BW>
 cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;
+    constexpr int RP = 2 * (((XT + 1) / 2) | 1);
     MarchArgs ma;
     const int bh = p->bin_h > 1 ? p->bin_h : 1;
     ma.bh = bh; ma.hh = bh / 2; ma.hw = BW / 2;
     ma.steps = (a.W + BW - 1 + XT - 1) / XT;
     ma.tile_rows = MR + bh - 1;
-    int words = (XT + 1) / 2;
-    if (words % 2 == 0) words += 1;
-    ma.rp = 2 * words;
-    const int threads = 32 * ((a.N + 1 + PL - 1) / PL);
-    ma.npos = ma.tile_rows * XT;
-    ma.groups = threads / ma.npos;
-    if (ma.groups < 1) return cudaErrorInvalidConfiguration;
-    if (ma.groups > a.N) ma.groups = a.N;
-    if ((a.N + ma.groups - 1) / ma.groups > 24) return cudaErrorInvalidConfiguration;
+    ma.isub = (int)a.sub; ma.idark = (int)a.dark;
+    const int npos = ma.tile_rows * XT;
+    ma.cw = (a.N + 1 + PL - 1) / PL;
+    if (ma.cw * 32 < MR * XT) ma.cw = (MR * XT + 31) / 32;
+    ma.lw = (npos + 32 * QMAX - 1) / (32 * QMAX);
+    if (ma.lw < 2 && npos > 32 * 3) ma.lw = 2;
+    const int threads = 32 * (ma.cw + ma.lw);
+    if (threads > 1024 || (long long)a.N * a.P >= 2147483647LL) return cudaErrorInvalidConfiguration;
     pb_ddrecip(bh, &ma.bh_hi, &ma.bh_lo);
     pb_ddrecip(BW, &ma.bw_hi, &ma.bw_lo);
     size_t off = hist_bytes(a);
-    ma.off_raw = (unsigned)off; off += ((size_t)a.N * ma.tile_rows * ma.rp * 2 + 15) & ~(size_t)15;
-    ma.off_T = (unsigned)off; off += ((size_t)ma.groups * ma.npos * 4 + 15) & ~(size_t)15;
+    ma.raw_bytes = (unsigned)(((size_t)a.N * ma.tile_rows * RP * 2 + 15) & ~(size_t)15);
+    ma.T_bytes = (unsigned)(((size_t)npos * 4 + 15) & ~(size_t)15);
+    ma.off_raw = (unsigned)off; off += 2 * (size_t)ma.raw_bytes;
+    ma.off_T = (unsigned)off; off += 2 * (size_t)ma.T_bytes;
     ma.off_f = (unsigned)off; off += (size_t)(a.N + 1) * MR * FP * 8;
     if (off > 227 * 1024) return cudaErrorInvalidConfiguration;
-    auto kern = k_march<UT, NH, BW>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off);
-    if (e != cudaSuccess) return e;
     dim3 grid((a.H + MR - 1) / MR, n_stacks);
-    kern<<<grid, threads, off, st>>>(a, bs, ma);
+    cudaError_t e;
+    if (bh == BW && BW > 1) {
+        auto kern = k_march<UT, NH, BW, true>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
+        kern<<<grid, threads, off, st>>>(a, bs, ma);
+    } else {
+        auto kern = k_march<UT, NH, BW, false>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
+        kern<<<grid, threads, off, st>>>(a, bs, ma);
+    }
     return cudaGetLastError();
 }
 
@@ -262,11 +330,18 @@ bool pb_march_supported(const pb_params *p) {
     if (sub != floor(sub) || p->dark != floor(p->dark) || sub < 0 || sub > 65535.0 || p->dark < 0 || p->dark > 65535.0) return false;
     if (p->bin_w > 8 || p->bin_h > 32) return false;
     if (p->N + 1 > 32 || p->N < 1) return false;
-    const int threads = 32 * ((p->N + 1 + PL - 1) / PL);
+    if ((long long)p->N * p->H * p->W >= 2147483647LL) return false;      // 32-bit element offsets in the loader
     const int bh = p->bin_h > 1 ? p->bin_h : 1, bw = p->bin_w > 1 ? p->bin_w : 1;
     const int xt = bw == 1 ? 8 : bw * ((8 + bw - 1) / bw);
-    if (threads < (MR + bh - 1) * xt || threads < MR * xt) return false;      // one loader group, one pixel thread per step pixel
-    return true;
+    int cw = (p->N + 1 + PL - 1) / PL;
+    if (cw * 32 < MR * xt) cw = (MR * xt + 31) / 32;
+    const int npos = (MR + bh - 1) * xt;
+    int lw = (npos + 32 * QMAX - 1) / (32 * QMAX);
+    if (lw < 2) lw = 2;
+    if (32 * (cw + lw) > 1024) return false;
+    const int rp = 2 * (((xt + 1) / 2) | 1), fp = (xt % 2) ? xt : xt + 1;
+    const size_t smem = 2 * ((size_t)p->N * (MR + bh - 1) * rp * 2 + 16) + 2 * ((size_t)npos * 4 + 16) + (size_t)(p->N + 1) * MR * fp * 8 + 16 * 1024;
+    return smem <= 227 * 1024;
 }
 
 cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches) {
