@@ -157,6 +157,7 @@ def main():
     import torch
     import torch.distributed as dist
     from polarimetry_b200 import AnalysisParams, Calibration, Engine, synth
+    from polarimetry_b200.batch import BatchAnalyzer
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -178,14 +179,13 @@ def main():
     for b in range(B):
         stacks[b].copy_(base[b % ndistinct])
     stacks = stacks.view(torch.uint16)
-    out = {}
+    runner = BatchAnalyzer(eng, p, cal)
+    out = runner._out
     launches0 = eng.launch_count()
 
     def step():
-        o = eng.analyze_batch(stacks, p, cal, want_intensity=False, out=out)
-        if world > 1:
-            dist.all_reduce(o['hist'])
-        return o
+        # this rank's shard of the batch; per-ROI histograms summed over ranks with one NCCL all-reduce (no-op at N=1)
+        return runner.run(stacks, reduce=world > 1)
 
     for _ in range(max(a.warmup, 3)):
         step()

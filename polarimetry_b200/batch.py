@@ -1,0 +1,63 @@
+"""Batch / time-series mode: many independent stacks (or frames) sharded over the GPUs of one box.
+
+One process per GPU (torchrun). Stacks are independent, so the data path needs no collective: each rank
+analyses its shard with its own `Engine`; only the per-ROI histograms (and the moment sums of the ROI
+statistics) are summed across ranks, with one all-reduce per batch over NCCL / NVLink. That sum is what the
+reference's `merge_histos` (PyPOLAR.py:2318-2384) computes when it concatenates the per-file values and
+histograms them once with the same bin edges.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous block partition of range(n_items): the first n_items % world ranks get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError('bad rank / world')
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place SUM over the ranks (no-op without an initialised process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def circular_moments(rho_deg: torch.Tensor, sel: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[N, sum cos 2rho, sum sin 2rho] in float64: the additive sufficient statistics of circularmean (PC:55-56)."""
+    r = rho_deg.to(torch.float64)
+    ok = torch.isfinite(r) if sel is None else (torch.isfinite(r) & sel.bool())
+    a = torch.deg2rad(2.0 * r[ok])
+    return torch.stack([ok.sum().to(torch.float64), torch.cos(a).sum(), torch.sin(a).sum()])
+
+
+def circular_mean_from_moments(m: torch.Tensor) -> float:
+    """mod(angle(mean(exp(2j rho))), 360) / 2 in degrees, from (reduced) moments."""
+    n, c, s = (float(x) for x in m)
+    if n == 0:
+        return float('nan')
+    return float(np.mod(np.degrees(np.arctan2(s / n, c / n)), 360.0) / 2.0)
+
+
+class BatchAnalyzer:
+    """Analyse this rank's shard of a batch and reduce the histograms over all ranks."""
+
+    def __init__(self, engine, params, calib=None, rois: Optional[Sequence[dict]] = None, per_roi: bool = False, group=None):
+        self.engine, self.params, self.calib, self.rois, self.per_roi, self.group = engine, params, calib, rois, per_roi, group
+        self._out = {}
+
+    def run(self, stacks_local, reduce: bool = True) -> dict:
+        """stacks_local: this rank's [B,N,H,W] stacks (device tensor). Returns the engine's output dict; o['hist'] holds the
+        histograms summed over the batch and, if reduce, over all ranks (int64 [1, n_groups, n_vars, nbins])."""
+        o = self.engine.analyze_batch(stacks_local, self.params, self.calib, self.rois, self.per_roi, want_intensity=False, out=self._out)
+        if reduce:
+            allreduce_sum_(o['hist'], self.group)
+        return o

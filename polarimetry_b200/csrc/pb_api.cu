@@ -67,6 +67,7 @@ struct pb_ctx {
     double *acc_dev = nullptr;        // stats accumulators
     cudaStream_t hs[2] = {nullptr, nullptr};
     cudaEvent_t hev[2] = {nullptr, nullptr};
+    cudaEvent_t ws_event = nullptr;   // recorded after the last kernel that used the shared workspace
 };
 
 #define CK(call)                                                                                     \
@@ -88,6 +89,19 @@ static int ws_reserve(pb_ctx *ctx, int slot, size_t bytes) {
     if (ctx->ws[slot]) { CK(cudaDeviceSynchronize()); CK(cudaFree(ctx->ws[slot])); ctx->ws[slot] = nullptr; ctx->ws_bytes[slot] = 0; }
     CK(cudaMalloc(&ctx->ws[slot], bytes));
     ctx->ws_bytes[slot] = bytes;
+    return PB_OK;
+}
+
+// The workspace (ws[0..4]) is shared by every call on this context: a call enqueued on another stream must not
+// start overwriting it while the previous user is still running. ws_acquire makes `st` wait for the previous user,
+// ws_release marks the end of this one.
+static int ws_acquire(pb_ctx *ctx, cudaStream_t st) {
+    if (!ctx->ws_event) CK(cudaEventCreateWithFlags(&ctx->ws_event, cudaEventDisableTiming));
+    else CK(cudaStreamWaitEvent(st, ctx->ws_event, 0));
+    return PB_OK;
+}
+static int ws_release(pb_ctx *ctx, cudaStream_t st) {
+    CK(cudaEventRecord(ctx->ws_event, st));
     return PB_OK;
 }
 
@@ -137,6 +151,7 @@ int pb_destroy(pb_ctx *ctx) {
     cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); if (ctx->hev[k]) cudaEventDestroy(ctx->hev[k]); }
+    if (ctx->ws_event) cudaEventDestroy(ctx->ws_event);
     delete ctx;
     return PB_OK;
 }
@@ -316,10 +331,11 @@ int pb_get_intensity(pb_ctx *ctx, const void *stack, int dtype, int N, int H, in
     if ((rc = ws_reserve(ctx, 2, sizeof(double) * P))) return rc;
     if ((rc = ws_reserve(ctx, 3, sizeof(double) * P))) return rc;
     double *a = (double *)ctx->ws[2], *b = (double *)ctx->ws[3], *res;
+    if ((rc = ws_acquire(ctx, st))) return rc;
     CK(pb_launch_isum(stack, dtype, a, P, N, dark, st)); ctx->launches++;
     if ((rc = run_box(ctx, a, b, 1, H, W, bh, bw, st, &res))) return rc;
     CK(cudaMemcpyAsync(out, res, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
-    return PB_OK;
+    return ws_release(ctx, st);
 }
 
 int pb_binning(pb_ctx *ctx, double *field, int planes, int H, int W, int bh, int bw, void *stream) {
@@ -332,9 +348,10 @@ int pb_binning(pb_ctx *ctx, double *field, int planes, int H, int W, int bh, int
     int rc;
     if ((rc = ws_reserve(ctx, 1, bytes))) return rc;
     double *res;
+    if ((rc = ws_acquire(ctx, st))) return rc;
     if ((rc = run_box(ctx, field, (double *)ctx->ws[1], planes, H, W, bh, bw, st, &res))) return rc;
     if (res != field) CK(cudaMemcpyAsync(field, res, bytes, cudaMemcpyDeviceToDevice, st));
-    return PB_OK;
+    return ws_release(ctx, st);
 }
 
 int pb_field(pb_ctx *ctx, const pb_params *p, const void *stack, double *field, void *stream) {
@@ -404,6 +421,7 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
     if ((rc = ws_reserve(ctx, 2, sizeof(double) * P))) return rc;
     if ((rc = ws_reserve(ctx, 3, sizeof(double) * P))) return rc;
     const size_t esz = dtype_size(p->dtype);
+    if ((rc = ws_acquire(ctx, st))) return rc;
     for (int s = 0; s < n_stacks; ++s) {
         const char *src = (const char *)stacks + (size_t)s * p->N * P * esz;
         double *Ires, *Fres;
@@ -416,7 +434,7 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
         if ((rc = launch_pixel(ctx, p, b, PB_F64, 1, st))) return rc;
         if (outs_host[s].intensity) CK(cudaMemcpyAsync(outs_host[s].intensity, Ires, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
     }
-    return PB_OK;
+    return ws_release(ctx, st);
 }
 
 int pb_fit_maps(pb_ctx *ctx, const pb_params *p, const double *field, const uint8_t *mask, double *fit, double *chi2, void *stream) {
@@ -436,11 +454,12 @@ int pb_histo(pb_ctx *ctx, const void *values, int is_f64, const uint8_t *sel, lo
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if ((rc = ws_reserve(ctx, 4, sizeof(double) * (PB_MAX_BINS + 1)))) return rc;
+    if ((rc = ws_acquire(ctx, st))) return rc;
     CK(cudaMemcpyAsync(ctx->ws[4], edges_host, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, st));
     CK(pb_launch_histo(values, is_f64, sel, n, is_rho, rot_fig, fold90, (const double *)ctx->ws[4], nbins,
                        (double)nbins / (edges_host[nbins] - edges_host[0]), counts, st));
     ctx->launches++;
-    return PB_OK;
+    return ws_release(ctx, st);
 }
 
 int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const uint8_t *sel, long n, int circular, double rot_fig,
@@ -451,6 +470,8 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     // circular & 1: circular statistics; circular & 2: apply the Rho re-wrap 2(v+rot)%360/2 first (PP:2744)
     const int circ = circular & 1, rewrap = (circular >> 1) & 1;
     double acc[5] = {0, 0, 0, 0, 0};
+    int rc0;
+    if ((rc0 = ws_acquire(ctx, st))) return rc0;
     CK(cudaMemsetAsync(ctx->acc_dev, 0, sizeof(double) * 8, st));
     CK(pb_launch_stats(1, values, rho, is_f64, sel, n, circ, rot_fig, rewrap, fold90, 0.0, ctx->acc_dev, st)); ctx->launches++;
     CK(cudaMemcpyAsync(acc, ctx->acc_dev, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
@@ -473,7 +494,7 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     double var = acc[4] / cnt - md * md;
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
-    return PB_OK;
+    return ws_release(ctx, st);
 }
 
 int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, int n_stacks, const uint32_t *roi_bits_host,
@@ -482,6 +503,7 @@ int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, in
     if (rc) return rc;
     if (!stacks_host || !outs_host || n_stacks < 1) return fail(ctx, PB_ERR_ARG, "pb_analyze_host: NULL argument");
     CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());   // synchronous API: earlier asynchronous work of this context may still use the workspace
     for (int k = 0; k < 2; ++k) {
         if (!ctx->hs[k]) CK(cudaStreamCreateWithFlags(&ctx->hs[k], cudaStreamNonBlocking));
         if (!ctx->hev[k]) CK(cudaEventCreateWithFlags(&ctx->hev[k], cudaEventDisableTiming));
