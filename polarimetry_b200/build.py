@@ -8,6 +8,7 @@ page maps to these files. nvcc cross-compiles without a GPU.
 """
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -36,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for s in SOURCES:
         o = PKG / 'build' / (s + '.o')
-        cmd = ['nvcc', *NVCC_FLAGS, '-c', str(CSRC / s), '-o', str(o)] + (['-Xptxas', '-v'] if verbose else [])
+        cmd = ['nvcc', *NVCC_FLAGS, *os.environ.get('PB_EXTRA_NVCC', '').split(), '-c', str(CSRC / s), '-o', str(o)] + (['-Xptxas', '-v'] if verbose else [])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(o))
     failed = False

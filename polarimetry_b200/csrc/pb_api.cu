@@ -45,6 +45,7 @@ struct pb_ctx {
     double2 *lut_dev = nullptr;
     double *grid_dev = nullptr;
     int lut_n = 0;
+    double grid_lo = -1.0, grid_hi = 1.0;
     double invk[16] = {0};
     int invk_rows = 0;
     Basis2 basis;
@@ -171,6 +172,7 @@ int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, co
     CK(cudaMemcpy(ctx->lut_dev, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->grid_dev, grid, sizeof(double) * n, cudaMemcpyHostToDevice));
     ctx->lut_n = n;
+    ctx->grid_lo = grid[0]; ctx->grid_hi = grid[n - 1];
     return PB_OK;
 }
 
@@ -284,6 +286,8 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     for (int r = 0; r < PB_MAX_ROIS; ++r) { a.roi_ilow[r] = ctx->roi_ilow[r]; a.group_bits[r] = ctx->group_bits[r]; }
     if (ctx->n_rois == 0) a.roi_ilow[0] = p->ilow;
     memcpy(a.invk, ctx->invk, sizeof(a.invk));
+    a.grid_lo = ctx->grid_lo; a.grid_hi = ctx->grid_hi; a.half_nm1 = 0.5 * (double)(ctx->lut_n - 1);
+    a.simple = 0;   // set by the callers once roi_bits / mask_in are known
 }
 
 // copy n output descriptors into the device ring; returns device pointer
@@ -401,6 +405,7 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
     PixArgs a;
     fill_args(ctx, p, a);
     a.roi_bits = roi_bits; a.edge = edge;
+    a.simple = (!roi_bits && ctx->n_rois == 0 && ctx->n_groups == 1) ? 1 : 0;
     const long long P = a.P;
     const std::string plan = plan_name(ctx, p);
     const pb_outputs *od;

@@ -18,7 +18,7 @@ struct Basis1 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES], kc2[PB_MAX_ANGLES],
 struct Basis2 { double c2[PB_MAX_ANGLES], s2[PB_MAX_ANGLES], c4[PB_MAX_ANGLES], s4[PB_MAX_ANGLES],
                        kc2[PB_MAX_ANGLES], ks2[PB_MAX_ANGLES], kc4[PB_MAX_ANGLES], ks4[PB_MAX_ANGLES]; };
 #ifndef PB_PIXEL_MIN_BLOCKS
-#define PB_PIXEL_MIN_BLOCKS 5
+#define PB_PIXEL_MIN_BLOCKS 8
 #endif
 template <int NH> struct BasisSel { using type = Basis1; };
 template <> struct BasisSel<2> { using type = Basis2; };
@@ -47,6 +47,8 @@ struct PixArgs {
     double rot_stick, rot_fig, ref_angle, chi2thr;
     double invN_hi, invN_lo, k2, dN;   // double-double 1/N, 2.0/N, (double)N (host computed)
     float thr_lo_n, thr_hi_n;          // chi2 threshold * N with -/+ 1e-5 margins (screening)
+    double grid_lo, grid_hi, half_nm1; // LUT grid end points and (n-1)/2
+    int simple;                        // no ROI bits, no incoming mask, one histogram group: whole-image thresholding
     double inv_bin_width[PB_MAX_VARS];
     double roi_ilow[PB_MAX_ROIS];
     uint32_t group_bits[PB_MAX_ROIS];

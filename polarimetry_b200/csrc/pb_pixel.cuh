@@ -47,7 +47,9 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
     if (d < e[k]) { do { --k; } while (k > 0 && d < e[k]); }
     else { while (k < nb - 1 && d >= e[k + 1]) ++k; }
     unsigned *c = h.cnt + var * nb + k;
-    if (a.n_groups == 1) {
+    if (a.simple) {
+        atomicAdd(c, 1u);
+    } else if (a.n_groups == 1) {
         if (bits & a.group_bits[0]) atomicAdd(c, 1u);
     } else {
         for (int g = 0; g < a.n_groups; ++g)
@@ -65,8 +67,10 @@ __device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double
 
 // disk-cone LUT cell and normalised distance along one axis: g[i] <= x < g[i+1], last cell closed
 // (scipy RegularGridInterpolator rule); t = (x - g[i]) / (g[i+1] - g[i]). Caller guarantees g[0] <= x <= g[n-1].
-__device__ __forceinline__ int lut_axis(const double *g, int n, double half_nm1, double x, double &t) {
-    int k = __double2int_rd(fma(x, half_nm1, half_nm1));       // ~ (x+1)(n-1)/2: off by at most one cell
+// The arithmetic guess floor((x+1)(n-1)/2) is exact up to one cell for a linspace grid; it is then corrected against
+// the real grid values (loops kept for arbitrary monotone grids, they run at most once for linspace).
+__device__ __forceinline__ int lut_axis(const double *__restrict__ g, int n, double half_nm1, double x, double &t) {
+    int k = __double2int_rd(fma(x, half_nm1, half_nm1));
     k = max(0, min(k, n - 2));
     double ga = __ldg(g + k), gb = __ldg(g + k + 1);
     if (x < ga) {
@@ -82,18 +86,16 @@ __device__ __forceinline__ int lut_axis(const double *g, int n, double half_nm1,
 // (SURVEY 8a row a6): v = 0 + V00 w00 + V01 w01 + V10 w10 + V11 w11, w = ((1)(1-t0))(1-t1) ... ; NaN corners propagate.
 __device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y, double &rho, double &psi) {
     rho = pb_nan(); psi = pb_nan();
-    const double *g = a.grid;
+    if (!(x >= a.grid_lo && x <= a.grid_hi && y >= a.grid_lo && y <= a.grid_hi)) return;   // out of range or NaN -> fill value NaN
     const int n = a.lut_n;
-    const double g0 = __ldg(g), g1 = __ldg(g + n - 1);
-    if (!(x >= g0 && x <= g1 && y >= g0 && y <= g1)) return;   // out of range or NaN -> fill value NaN
-    const double half_nm1 = 0.5 * (double)(n - 1);
     double t0, t1;
-    const int i0 = lut_axis(g, n, half_nm1, x, t0), i1 = lut_axis(g, n, half_nm1, y, t1);
+    const int i0 = lut_axis(a.grid, n, a.half_nm1, x, t0), i1 = lut_axis(a.grid, n, a.half_nm1, y, t1);
     const double u0 = 1.0 - t0, u1 = 1.0 - t1;
     const double w00 = u0 * u1, w01 = u0 * t1, w10 = t0 * u1, w11 = t0 * t1;    // (1.0 * u0) == u0 exactly
-    const double2 *T = a.lut + (long long)i0 * n + i1;
+    const double2 *T = a.lut + (i0 * n + i1);
     const double2 v00 = __ldg(T), v01 = __ldg(T + 1), v10 = __ldg(T + n), v11 = __ldg(T + n + 1);
-    double r = 0.0 + v00.x * w00, q = 0.0 + v00.y * w00;
+    // 0.0 + p == p for every p that can matter here (p = -0.0 only for a zero table entry times a zero weight)
+    double r = v00.x * w00, q = v00.y * w00;
     r = r + v01.x * w01; q = q + v01.y * w01;
     r = r + v10.x * w10; q = q + v10.y * w10;
     r = r + v11.x * w11; q = q + v11.y * w11;
@@ -145,8 +147,13 @@ __device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, d
     HarmPix h;
     h.a0 = pb_nan(); h.a2r = h.a2i = h.a4r = h.a4i = 0.0;
     h.need = false;
-    h.bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
-    h.m = a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, h.bits, I);
+    if (a.simple) {                                            // whole image, one threshold (PP:2875-2876)
+        h.bits = 1u;
+        h.m = I >= a.roi_ilow[0];
+    } else {
+        h.bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
+        h.m = a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, h.bits, I);
+    }
     if (!h.m) return h;
     // S0 / N correctly rounded without a division: fma(S0, rhi, S0*rlo) with (rhi, rlo) the double-double 1/N
     // (tests/test_shortcuts.py; x/N is never within 2^-60 of a rounding boundary, the approximation error is 2^-105)
