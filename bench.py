@@ -29,6 +29,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W, N = 2048, 2048, 18
+WORKLOADS = {'1pf': ('1PF', 18), 'shg': ('SHG', 36), '4polar3d': ('4POLAR 3D', 4)}   # BASELINE configs[3] (headline), [1], [2]
 DISK = ROOT / 'tests' / 'golden' / 'calib' / 'Disk_Ga0_Pa0_Ta0_Gb0_Pb0_Tb0_Gc0_Pc0_Tc0.npz'
 DARK, ILOW = 480.0, 40000.0
 OUT_BYTES_PER_PIXEL = 13      # rho f32 + psi f32 + intmap f32 + mask u8
@@ -49,7 +50,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -120,12 +121,12 @@ def run_reference_arm(a):
     workers = host_workers()
     vals = []
     for s in range(a.warmup + a.steps):
-        v, dt = cpu_sample(bins, workers)
+        v, dt = cpu_sample(bins, workers, per_worker=2)
         if s >= a.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-    sample = f'{workers} stacks 1024x1024x18 uint16 per step, one per worker process (oracle/restate.py = the reference\'s NumPy/SciPy statements)'
+    sample = f'{2 * workers} stacks 1024x1024x18 uint16 per step, two per worker process (oracle/restate.py = the reference\'s NumPy/SciPy statements)'
     line = {'impl': 'reference', 'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(a, None),
@@ -135,21 +136,25 @@ def run_reference_arm(a):
 
 
 def workload_config(a, batch):
-    return {'workload': f'1PF batch of {H}x{W}x{N} uint16 stacks, dark {DARK:.0f}, bin {a.bin}x{a.bin}, disk-cone LUT (no distortion), '
-                        f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
-            'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
+    wl = getattr(a, 'workload', '1pf')
+    text = {'1pf': f'1PF batch of {H}x{W}x18 uint16 stacks, dark {DARK:.0f}, bin {a.bin}x{a.bin}, disk-cone LUT (no distortion), '
+                   f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
+            'shg': f'SHG batch of {H}x{W}x36 uint16 stacks (BASELINE configs[1]), bin {a.bin}x{a.bin}, rho/S2/S4/S_SHG/intensity maps f32 + mask + histograms',
+            '4polar3d': f'4POLAR 3D batch of 4x{H}x{W} uint16 (BASELINE configs[2]), bin {a.bin}x{a.bin}, rho/psi/eta/intensity maps f32 + mask + histograms'}[wl]
+    return {'workload': text, 'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--bin', type=int, default=int(os.environ.get('PB_BENCH_BIN', '3')))
     ap.add_argument('--batch', type=int, default=int(os.environ.get('PB_BENCH_BATCH', '16')), help='stacks resident per GPU')
     ap.add_argument('--e2e-batch', type=int, default=4)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--workload', default='1pf', choices=sorted(WORKLOADS), help='1pf = the headline (BASELINE configs[3]); shg / 4polar3d = configs[1] / [2], reported for information')
     a = ap.parse_args()
     if a.impl == 'reference':
         return run_reference_arm(a)
@@ -167,14 +172,27 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     dev = torch.device('cuda', local)
     eng = Engine(local)
+    global N
+    method, N = WORKLOADS[a.workload]
     d = np.load(DISK)
-    cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-    p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ILOW, out_dtype='float32')
+    if method == '1PF':
+        cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ILOW, out_dtype='float32')
+        gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed)
+    elif method == 'SHG':
+        cal = None
+        p = AnalysisParams(method='SHG', dark=0.0, bins=(a.bin, a.bin), ilow=40000.0, out_dtype='float32')
+        gen = lambda seed: synth.stack_4harm(H, W, N, seed=seed)
+    else:
+        cal = Calibration.from_K(synth.K_TH_3D)
+        p = AnalysisParams(method='4POLAR 3D', dark=0.0, bins=(a.bin, a.bin), ilow=1000.0, out_dtype='float32')
+        gen = lambda seed: synth.stack_4polar(H, W, seed=seed, three_d=True)
+    out_bpp = {'1PF': 13, 'SHG': 21, '4POLAR 3D': 17}[method]
 
     # synthetic stacks: a few distinct seeded G1 stacks per rank, tiled to the resident batch (19 MB/stack of host RNG work each)
     B = a.batch
     ndistinct = min(B, 4)
-    base = [torch.from_numpy(synth.stack_1pf(H, W, N, seed=1000 * rank + k).view(np.int16)) for k in range(ndistinct)]
+    base = [torch.from_numpy(gen(1000 * rank + k).view(np.int16)) for k in range(ndistinct)]
     stacks = torch.empty((B, N, H, W), dtype=torch.int16, device=dev)
     for b in range(B):
         stacks[b].copy_(base[b % ndistinct])
@@ -216,7 +234,7 @@ def main():
 
     # roofline of the dominant kernel: algorithmic bytes of one launch / its CUDA-event duration (median step)
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = B * (H * W * N * 2 + H * W * OUT_BYTES_PER_PIXEL)
+    alg_bytes = B * (H * W * N * 2 + H * W * out_bpp)
     kern_ms = float(np.median(step_ms))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
@@ -257,15 +275,15 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = Be * H * W * N * world * e2e_steps / float(te.item()) / 1e6
     e2e = {'value': e2e_val, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': Be * H * W * N * 2,
-           'd2h_bytes_per_step': Be * (H * W * OUT_BYTES_PER_PIXEL) + 2 * 60 * 8, 'stacks_per_step': Be,
+           'd2h_bytes_per_step': Be * (H * W * out_bpp) + 2 * 60 * 8, 'stacks_per_step': Be,
            'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu:
+    if rank == 0 and world == 1 and not a.no_cpu and a.workload == '1pf':
         workers = host_workers()
-        v, dt = cpu_sample((a.bin, a.bin), workers)
+        v, dt = cpu_sample((a.bin, a.bin), workers, per_worker=4)
         cpu = {'value': v, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port',
-               'sample': f'{workers} stacks 1024x1024x18 (one per worker process) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
+               'sample': f'{4 * workers} stacks 1024x1024x18 (4 per worker process, {workers} processes) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
     if rank == 0:
         line = {'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
