@@ -138,8 +138,7 @@ __global__ void __maxnreg__(80) k_march(PixArgs a, typename BasisSel<NH>::type b
                 for (int q = 0; q < QMAX; ++q)
                     if (jj[q] >= 0) Tb[ltid + q * LT] = tsum[q];
             }
-            __syncthreads();                 // (1) buffer t&1 complete (and, for t >= 1, phase B of step t-1 done)
-            if (t < steps) __syncthreads();  // (2) phase A of step t done
+            __syncthreads();                 // end-of-step barrier: buffer t&1 complete, step t-1 fully consumed
         }
     } else {
         // =========================== compute warps ===========================
@@ -159,7 +158,7 @@ __global__ void __maxnreg__(80) k_march(PixArgs a, typename BasisSel<NH>::type b
         const bool pix = tid < MR * XT && (y0 + pr) < H;
         const double *const pfp = fbuf + pr * FP + pj;
         const bool f64 = a.flags & PB_FLAG_OUT_F64;
-        __syncthreads();                      // (1) of t = 0
+        __syncthreads();                      // tile of step 0 in place
         for (int t = 0; t < steps; ++t) {
             const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
             const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
@@ -215,42 +214,53 @@ __global__ void __maxnreg__(80) k_march(PixArgs a, typename BasisSel<NH>::type b
                     }
                 }
             }
-            __syncthreads();                  // (2) fbuf of step t complete
+            asm volatile("bar.sync 1, %0;" ::"r"(ma.cw * 32) : "memory");   // compute warps only: fbuf of step t complete
             // ---- phase B: the pixels completed by this step
             const int k = t * XT + pj - (BW - 1);
             if (pix && k >= 0 && k < W) {
-                double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
-                const double *fp = pfp;
-#pragma unroll 6
-                for (int i = 0; i < N; ++i) {
-                    const double f = *fp;
-                    fp += MR * FP;
-                    S0 = S0 + f;
-                    Sc = Sc + f * bs.c2[i];
-                    Ss = Ss + f * bs.s2[i];
-                    if constexpr (NH == 2) {
-                        Sc4 = Sc4 + f * bs.c4[i];
-                        Ss4 = Ss4 + f * bs.s4[i];
-                    }
-                    Sff = fma(f, f, Sff);                        // screening only
-                }
-                const double I = *fp;                            // plane N: the binned total intensity
                 const long long p = (long long)(y0 + pr) * W + k;
-                HarmPix hp = harm_stage_a<NH>(a, p, S0, Sc, Ss, Sc4, Ss4, Sff, I);
-                if (hp.need) {
-                    ExactAcc ex;
-                    ex.init();
+                const double I = pfp[N * (MR * FP)];             // plane N: the binned total intensity
+                // the threshold / ROI test needs only I: pixels that fail it skip the harmonic sums altogether
+                // (their maps are NaN whatever the sums are, PP:3017-3025 / PP:3052)
+                bool cand;
+                if (a.simple) cand = I >= a.roi_ilow[0];
+                else if (a.mask_in) cand = __ldg(a.mask_in + p) != 0;
+                else cand = roi_pass(a, a.roi_bits ? __ldg(a.roi_bits + p) : 1u, I);
+                PixOut o;
+                o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
+                o.m = false;
+                if (cand) {
+                    double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
+                    const double *fp = pfp;
+#pragma unroll 6
                     for (int i = 0; i < N; ++i) {
-                        double c4 = 0.0, s4 = 0.0;
-                        if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-                        ex.template step<NH>(hp, pfp[i * (MR * FP)], bs.c2[i], bs.s2[i], c4, s4);
+                        const double f = *fp;
+                        fp += MR * FP;
+                        S0 = S0 + f;
+                        Sc = Sc + f * bs.c2[i];
+                        Ss = Ss + f * bs.s2[i];
+                        if constexpr (NH == 2) {
+                            Sc4 = Sc4 + f * bs.c4[i];
+                            Ss4 = Ss4 + f * bs.s4[i];
+                        }
+                        Sff = fma(f, f, Sff);                    // screening only
                     }
-                    hp.m = ex.decide(a);
+                    HarmPix hp = harm_stage_a<NH>(a, p, S0, Sc, Ss, Sc4, Ss4, Sff, I);
+                    if (hp.need) {
+                        ExactAcc ex;
+                        ex.init();
+                        for (int i = 0; i < N; ++i) {
+                            double c4 = 0.0, s4 = 0.0;
+                            if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
+                            ex.template step<NH>(hp, pfp[i * (MR * FP)], bs.c2[i], bs.s2[i], c4, s4);
+                        }
+                        hp.m = ex.decide(a);
+                    }
+                    o = harm_stage_b<NH>(a, hs, do_hist, hp);
                 }
-                const PixOut o = harm_stage_b<NH>(a, hs, do_hist, hp);
                 store_pixel<NH>(a, out, p, o, I, f64);
             }
-            __syncthreads();                  // (1) of step t+1: fbuf free again, next tile in place
+            __syncthreads();                  // end-of-step barrier (all warps): fbuf free again, tile of step t+1 in place
         }
     }
     if (do_hist) hist_flush(a, hs, out.hist);
