@@ -141,7 +141,7 @@ def workload_config(a, batch):
                    f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
             'shg': f'SHG batch of {H}x{W}x36 uint16 stacks (BASELINE configs[1]), bin {a.bin}x{a.bin}, rho/S2/S4/S_SHG/intensity maps f32 + mask + histograms',
             '4polar3d': f'4POLAR 3D batch of 4x{H}x{W} uint16 (BASELINE configs[2]), bin {a.bin}x{a.bin}, rho/psi/eta/intensity maps f32 + mask + histograms'}[wl]
-    return {'workload': text, 'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
+    return {'workload': text, 'ilow': getattr(a, 'ilow', ILOW), 'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
 
 
 def main():
@@ -154,6 +154,7 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=4)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--ilow', type=float, default=ILOW, help='intensity threshold (1pf workload); 0 keeps every pixel')
     ap.add_argument('--workload', default='1pf', choices=sorted(WORKLOADS), help='1pf = the headline (BASELINE configs[3]); shg / 4polar3d = configs[1] / [2], reported for information')
     a = ap.parse_args()
     if a.impl == 'reference':
@@ -177,7 +178,7 @@ def main():
     d = np.load(DISK)
     if method == '1PF':
         cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ILOW, out_dtype='float32')
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=a.ilow, out_dtype='float32')
         gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed)
     elif method == 'SHG':
         cal = None
@@ -231,6 +232,7 @@ def main():
     px_angles_step = B * H * W * N * world
     value = px_angles_step * a.steps / (total_ms * 1e-3) / 1e6
     plan = out['plan']
+    valid_frac = float(out['mask'].float().mean().item())
 
     # roofline of the dominant kernel: algorithmic bytes of one launch / its CUDA-event duration (median step)
     peak, peak_src = measured_peak_gbs()
@@ -287,7 +289,7 @@ def main():
     if rank == 0:
         line = {'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-                'data': 'synthetic', 'config': workload_config(a, B), 'plan': plan, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+                'data': 'synthetic', 'config': dict(workload_config(a, B), valid_pixel_fraction=round(valid_frac, 4)), 'plan': plan, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
                 'gpu_launches': int(launches_per_step * a.steps), 'clocks': clocks}
         print(json.dumps(line))
     if world > 1:

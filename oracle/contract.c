@@ -333,3 +333,26 @@ long pc_check_magic_product(double c, long count, uint64_t seed) {
     }
     return bad;
 }
+
+/* d / h == q with y = RN(1/h), q0 = RN(d*y), r = fma(-q0, h, d) (exact), q = fma(r, y, q0)  (Markstein's correctly
+ * rounded division from a correctly rounded reciprocal). Used for the LUT cell coordinate t = (x - g[i]) / (g[i+1] - g[i])
+ * where h takes the n-1 values of the grid spacing. Returns mismatches over `count` numerators 0 <= d <= 1.5 h. */
+long pc_check_markstein_div(double h, long count, uint64_t seed) {
+    const double y = 1.0 / h;
+    long bad = 0;
+    uint64_t s = seed ? seed : 99991ULL;
+    for (long k = 0; k < count; ++k) {
+        uint64_t r = rng_next(&s);
+        double u = (double)(r >> 11) * (1.0 / 9007199254740992.0);        /* [0,1) */
+        double d;
+        switch (k & 3) {
+        case 0: d = u * h; break;
+        case 1: d = u * h * 1.5; break;
+        case 2: d = ldexp(u, -(int)(r % 40)) * h; break;                    /* tiny numerators */
+        default: d = (double)(r % 1000003ULL) * (h / 1000003.0); break;
+        }
+        double q0 = d * y, rr = fma(-q0, h, d), q = fma(rr, y, q0);
+        if (q != d / h) ++bad;
+    }
+    return bad;
+}

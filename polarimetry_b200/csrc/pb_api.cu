@@ -44,6 +44,7 @@ struct pb_ctx {
     // calibration
     double2 *lut_dev = nullptr;
     double *grid_dev = nullptr;
+    double2 *hy_dev = nullptr;
     int lut_n = 0;
     double grid_lo = -1.0, grid_hi = 1.0;
     double invk[16] = {0};
@@ -149,7 +150,7 @@ int pb_destroy(pb_ctx *ctx) {
     if (!ctx) return PB_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
+    cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); if (ctx->hev[k]) cudaEventDestroy(ctx->hev[k]); }
     if (ctx->ws_event) cudaEventDestroy(ctx->ws_event);
@@ -166,7 +167,15 @@ int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, co
     std::vector<double2> t((size_t)n * n);
     for (size_t k = 0; k < t.size(); ++k) { t[k].x = rho[k]; t[k].y = psi[k]; }
     CK(cudaDeviceSynchronize());
-    if (ctx->lut_dev) { cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); ctx->lut_dev = nullptr; ctx->grid_dev = nullptr; }
+    if (ctx->lut_dev) { cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); ctx->lut_dev = nullptr; ctx->grid_dev = nullptr; ctx->hy_dev = nullptr; }
+    std::vector<double2> hy((size_t)n - 1);
+    for (int k = 0; k + 1 < n; ++k) {
+        hy[k].x = grid[k + 1] - grid[k];       // the reference's (grid[i+1] - grid[i]), one rounding
+        hy[k].y = 1.0 / hy[k].x;               // correctly rounded reciprocal
+        if (!(hy[k].x > 0.0)) return fail(ctx, PB_ERR_ARG, "pb_set_diskcone: grid must be strictly increasing");
+    }
+    CK(cudaMalloc(&ctx->hy_dev, sizeof(double2) * hy.size()));
+    CK(cudaMemcpy(ctx->hy_dev, hy.data(), sizeof(double2) * hy.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&ctx->lut_dev, sizeof(double2) * t.size()));
     CK(cudaMalloc(&ctx->grid_dev, sizeof(double) * n));
     CK(cudaMemcpy(ctx->lut_dev, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice));
@@ -261,7 +270,7 @@ static int check_params(pb_ctx *ctx, const pb_params *p) {
 
 static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     memset(&a, 0, sizeof(a));
-    a.lut = ctx->lut_dev; a.grid = ctx->grid_dev; a.lut_n = ctx->lut_n;
+    a.lut = ctx->lut_dev; a.grid = ctx->grid_dev; a.lut_hy = ctx->hy_dev; a.lut_n = ctx->lut_n;
     a.hist_edges = ctx->edges_dev;
     a.N = p->N; a.H = p->H; a.W = p->W; a.P = (long long)p->H * p->W;
     a.method = p->method;

@@ -34,6 +34,7 @@ struct PixArgs {
     const pb_outputs *outs;     // device array [n_stacks]
     const double2 *lut;         // [n*n] (rho, psi) interleaved
     const double *grid;         // [n]
+    const double2 *lut_hy;      // [n-1] (h = g[k+1]-g[k], RN(1/h)) per cell
     const double *hist_edges;   // [n_vars][nbins+1]
     int lut_n;
     int N, H, W;

@@ -30,7 +30,7 @@ namespace {
 
 constexpr int MR = 32;     // rows per CTA (= lanes of a chain warp)
 constexpr int PL = 2;      // planes (lines) per chain thread
-constexpr int QMAX = 6;    // tile positions per loader thread
+constexpr int QMAX = 4;    // tile positions per loader thread
 
 struct MarchArgs {
     int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
@@ -48,7 +48,7 @@ template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr i
 
 // SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
 template <typename UT, int NH, int BW, bool SQ>
-__global__ void __maxnreg__(80) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
+__global__ void __maxnreg__(76) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
     constexpr int RW = ((XT + 1) / 2) | 1;              // raw tile row pitch in 32-bit words (odd: conflict-free chain loads)

@@ -69,7 +69,7 @@ __device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double
 // (scipy RegularGridInterpolator rule); t = (x - g[i]) / (g[i+1] - g[i]). Caller guarantees g[0] <= x <= g[n-1].
 // The arithmetic guess floor((x+1)(n-1)/2) is exact up to one cell for a linspace grid; it is then corrected against
 // the real grid values (loops kept for arbitrary monotone grids, they run at most once for linspace).
-__device__ __forceinline__ int lut_axis(const double *__restrict__ g, int n, double half_nm1, double x, double &t) {
+__device__ __forceinline__ int lut_axis(const double *__restrict__ g, const double2 *__restrict__ hy, int n, double half_nm1, double x, double &t) {
     int k = __double2int_rd(fma(x, half_nm1, half_nm1));
     k = max(0, min(k, n - 2));
     double ga = __ldg(g + k), gb = __ldg(g + k + 1);
@@ -78,7 +78,11 @@ __device__ __forceinline__ int lut_axis(const double *__restrict__ g, int n, dou
     } else if (x >= gb && k < n - 2) {
         do { ++k; ga = gb; gb = __ldg(g + k + 1); } while (k < n - 2 && x >= gb);
     }
-    t = (x - ga) / (gb - ga);
+    // t = (x - ga) / (gb - ga), correctly rounded from the tabulated spacing h = gb - ga and y = RN(1/h)
+    // (Markstein: q0 = RN(d y), r = d - q0 h exactly, t = RN(q0 + r y); tests/test_shortcuts.py)
+    const double2 c = __ldg(hy + k);
+    const double d = x - ga, q0 = d * c.y;
+    t = fma(fma(-q0, c.x, d), c.y, q0);
     return k;
 }
 
@@ -89,7 +93,7 @@ __device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y,
     if (!(x >= a.grid_lo && x <= a.grid_hi && y >= a.grid_lo && y <= a.grid_hi)) return;   // out of range or NaN -> fill value NaN
     const int n = a.lut_n;
     double t0, t1;
-    const int i0 = lut_axis(a.grid, n, a.half_nm1, x, t0), i1 = lut_axis(a.grid, n, a.half_nm1, y, t1);
+    const int i0 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, x, t0), i1 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, y, t1);
     const double u0 = 1.0 - t0, u1 = 1.0 - t1;
     const double w00 = u0 * u1, w01 = u0 * t1, w10 = t0 * u1, w11 = t0 * t1;    // (1.0 * u0) == u0 exactly
     const double2 *T = a.lut + (i0 * n + i1);

@@ -24,3 +24,13 @@ def test_magic_product_equals_rounded_product():
     e2 = np.exp(2j * np.deg2rad(-np.linspace(0, 180, 18, endpoint=False) + 17.5))
     for c in list(e2.real) + list(e2.imag) + list(rng.uniform(-1, 1, 20)) + [1.0, -1.0, 0.0, 6.123233995736766e-17]:
         assert lib.pc_check_magic_product(C.c_double(float(c)), C.c_long(200_000), C.c_uint64(int(abs(c) * 1e9) + 3)) == 0
+
+
+def test_markstein_division_by_grid_spacing():
+    """t = (x - g[i]) / (g[i+1] - g[i]) via the reciprocal table: exact for every spacing of linspace(-1, 1, n)."""
+    lib = ct.lib()
+    lib.pc_check_markstein_div.restype = C.c_long
+    for n in (401, 201, 1001):
+        g = np.linspace(-1, 1, n)
+        for h in np.unique(np.diff(g)):
+            assert lib.pc_check_markstein_div(C.c_double(float(h)), C.c_long(400_000), C.c_uint64(int(h * 1e12) % 2**31 + 5)) == 0
