@@ -30,7 +30,8 @@ namespace {
 
 constexpr int MR = 32;     // rows per CTA (= lanes of a chain warp)
 constexpr int PL = 2;      // planes (lines) per chain thread
-constexpr int QMAX = 4;    // tile positions per loader thread
+constexpr int QMAX = 2;    // tile positions per loader thread
+constexpr int LA = 6;      // angle planes per loader batch
 
 struct MarchArgs {
     int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
@@ -48,7 +49,7 @@ template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr i
 
 // SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
 template <typename UT, int NH, int BW, bool SQ>
-__global__ void __maxnreg__(76) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
+__global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
     constexpr int RW = ((XT + 1) / 2) | 1;              // raw tile row pitch in 32-bit words (odd: conflict-free chain loads)
@@ -74,6 +75,7 @@ __global__ void __maxnreg__(76) k_march(PixArgs a, typename BasisSel<NH>::type b
         // raw stack -> shared memory, dark-subtracted and clamped (PP:2953), for step t+1 while the compute warps work on step t;
         // also the per-position total-intensity sums sum_i max(v - dark, 0) (PC:261) for the threshold image.
         const UT *stack = reinterpret_cast<const UT *>(a.stack) + (long long)blockIdx.y * a.stack_stride;
+        asm volatile("" : "+l"(stack));
         const int ltid = tid - ma.cw * 32, LT = ma.lw * 32;
         const int isub = ma.isub, idark = ma.idark;
         const bool sep = isub != idark;
@@ -101,38 +103,48 @@ __global__ void __maxnreg__(76) k_march(PixArgs a, typename BasisSel<NH>::type b
                     off[q] = rowoff[q] + (unsigned)(jj[q] >= 0 ? pb_reflect(t * XT + jj[q] - ma.hw, W) : 0);
                     tsum[q] = 0;
                 }
-                unsigned ip = 0;
+                // running plane pointers kept opaque so that the 64-bit stack base is not re-derived for every load:
+                // per element one address IMAD.WIDE, the load, the fused subtract/clamp, the store and half an add
+                const UT *bp = stack;
                 uint16_t *dst = rawb;
                 int i = 0;
-                for (; i + 2 <= N; i += 2) {
-                    unsigned v0[QMAX], v1[QMAX];
+                for (; i + LA <= N; i += LA) {            // LA planes x QMAX positions of loads in flight before any is consumed
+                    asm volatile("" : "+l"(bp));
+                    unsigned v[LA][QMAX];
+                    const UT *b = bp;
 #pragma unroll
-                    for (int q = 0; q < QMAX; ++q) {
-                        v0[q] = (unsigned)__ldg(stack + (off[q] + ip));
-                        v1[q] = (unsigned)__ldg(stack + (off[q] + ip + uP));
+                    for (int l = 0; l < LA; ++l) {
+#pragma unroll
+                        for (int q = 0; q < QMAX; ++q) v[l][q] = (unsigned)__ldg(b + off[q]);
+                        b += uP;
                     }
 #pragma unroll
                     for (int q = 0; q < QMAX; ++q) {
                         if (jj[q] >= 0) {
-                            const int f0 = max((int)v0[q] - isub, 0), f1 = max((int)v1[q] - isub, 0);
-                            dst[soff[q]] = (uint16_t)f0;
-                            dst[soff[q] + plane_pitch] = (uint16_t)f1;
-                            tsum[q] += sep ? max((int)v0[q] - idark, 0) + max((int)v1[q] - idark, 0) : f0 + f1;
+#pragma unroll
+                            for (int l = 0; l < LA; ++l) {
+                                const int f = max((int)v[l][q] - isub, 0);
+                                dst[soff[q] + l * plane_pitch] = (uint16_t)f;
+                                tsum[q] += sep ? max((int)v[l][q] - idark, 0) : f;
+                            }
                         }
                     }
-                    ip += 2 * uP;
-                    dst += 2 * plane_pitch;
+                    bp += (size_t)LA * uP;
+                    dst += LA * plane_pitch;
                 }
-                if (i < N) {
+                for (; i < N; ++i) {
+                    asm volatile("" : "+l"(bp));
 #pragma unroll
                     for (int q = 0; q < QMAX; ++q) {
                         if (jj[q] >= 0) {
-                            const int v = (int)__ldg(stack + (off[q] + ip));
+                            const int v = (int)__ldg(bp + off[q]);
                             const int f = max(v - isub, 0);
                             dst[soff[q]] = (uint16_t)f;
                             tsum[q] += sep ? max(v - idark, 0) : f;
                         }
                     }
+                    bp += uP;
+                    dst += plane_pitch;
                 }
 #pragma unroll
                 for (int q = 0; q < QMAX; ++q)
