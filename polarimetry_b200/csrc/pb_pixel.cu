@@ -94,7 +94,7 @@ __device__ __forceinline__ void store4(void *base, long long p, double x0, doubl
 //   MODE 1: integer fast path -- uint8/uint16 stack, integer-valued dark and dark+removed, no sqrt.
 //   MODE 0: generic -- fp64 pre-processing (float input, fractional dark, CARS sqrt, or an already binned double field).
 template <typename T, int NH, int PX, int MODE>
-__global__ void __launch_bounds__(128, PB_PIXEL_MIN_BLOCKS) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
+__global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
     extern __shared__ __align__(16) unsigned char smem[];
     const pb_outputs out = a.outs[blockIdx.y];
     const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
@@ -174,39 +174,39 @@ __global__ void __launch_bounds__(128, PB_PIXEL_MIN_BLOCKS) k_pixel_harm(PixArgs
             }
         }
         const bool f64 = a.flags & PB_FLAG_OUT_F64;
+        // Epilogue, one pixel at a time. For the 4-harmonic modalities (atan2 / hypot / cos: ~1000 instructions per pixel)
+        // the loop is ROLLED: unrolled PX times it overflows the instruction cache (measured: -15 % time when rolled; its
+        // inputs/outputs then live in small dynamically indexed local arrays). For 1PF the unrolled form is faster
+        // (independent pixels interleave and hide the fp64 latencies; measured +13 % when rolled), so it stays unrolled.
+        struct PixIn { double S0, Sc, Ss, Sc4, Ss4, Sff, I; };
+        PixIn in[PX];
         PixOut o[PX];
-        HarmPix hp[PX];
         double Iv[PX];
-        bool any_need = false;
 #pragma unroll
         for (int k = 0; k < PX; ++k) {
             Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
-            hp[k] = harm_stage_a<NH>(a, p0 + k, S0d[k], Sc[k], Ss[k], Sc4[k], Ss4[k], Sffd[k], Iv[k]);
-            any_need |= hp[k].need;
+            in[k].S0 = S0d[k]; in[k].Sc = Sc[k]; in[k].Ss = Ss[k]; in[k].Sc4 = Sc4[k]; in[k].Ss4 = Ss4[k]; in[k].Sff = Sffd[k]; in[k].I = Iv[k];
         }
-        if (any_need) {
-            // rare path: the reference's fp64 fit/chi2 loop for the undecided pixels of this thread (stack re-read, L1/L2 hits)
-            ExactAcc ex[PX];
-#pragma unroll
-            for (int k = 0; k < PX; ++k) ex[k].init();
-            for (int i = 0; i < N; ++i) {
-                double v[PX];
-                VecLoad<T, PX>::ld(base + (long long)i * P, v);
-                double c4 = 0.0, s4 = 0.0;
-                if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-#pragma unroll
-                for (int k = 0; k < PX; ++k) {
-                    double f = v[k];
+#pragma unroll(NH == 1 ? PX : 1)
+        for (int k = 0; k < PX; ++k) {
+            const PixIn x = in[k];
+            HarmPix hp = harm_stage_a<NH>(a, p0 + k, x.S0, x.Sc, x.Ss, x.Sc4, x.Ss4, x.Sff, x.I);
+            if (hp.need) {
+                // rare path: the reference's fp64 fit/chi2 loop for an undecided pixel (stack re-read, L1/L2 hits)
+                ExactAcc ex;
+                ex.init();
+                const T *px = base + k;
+                for (int i = 0; i < N; ++i) {
+                    double f = (double)__ldg(px + (long long)i * P);
                     if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
-                    ex[k].template step<NH>(hp[k], f, bs.c2[i], bs.s2[i], c4, s4);
+                    double c4 = 0.0, s4 = 0.0;
+                    if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
+                    ex.template step<NH>(hp, f, bs.c2[i], bs.s2[i], c4, s4);
                 }
+                hp.m = ex.decide(a);
             }
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-                if (hp[k].need) hp[k].m = ex[k].decide(a);
+            o[k] = harm_stage_b<NH>(a, hs, do_hist, hp);
         }
-#pragma unroll
-        for (int k = 0; k < PX; ++k) o[k] = harm_stage_b<NH>(a, hs, do_hist, hp[k]);
         if constexpr (PX == 4) {
             store4(out.var[0], p0, o[0].v0, o[1].v0, o[2].v0, o[3].v0, f64);
             store4(out.var[1], p0, o[0].v1, o[1].v1, o[2].v1, o[3].v1, f64);
