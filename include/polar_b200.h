@@ -137,6 +137,10 @@ int pb_histo(pb_ctx *ctx, const void *values_dev, int is_f64, const uint8_t *sel
 int pb_stats(pb_ctx *ctx, const void *values_dev, const void *rho_dev, int is_f64, const uint8_t *sel_dev, long n, int circular,
              double rotation_fig, int fold90, double *out_host, void *stream);
 
+/* "next" row N2: replaces Stack.compute_dark (PC:266-278): the mean over all angles of the non-zero samples of
+ * the size_cell x size_cell cell whose first-angle non-zero mean is smallest. Integer stacks. Synchronises `stream`. */
+int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H, int W, int size_cell, double *dark_host, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
 long pb_launch_count(const pb_ctx *ctx);

@@ -47,6 +47,7 @@ EXPORTS = {
     'pb_fit_maps': (C.c_int, [C.c_void_p, C.POINTER(PbParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb_histo': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pb_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    'pb_compute_dark': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     'pb_launch_count': (C.c_long, [C.c_void_p]),
     'pb_plan': (C.c_char_p, [C.c_void_p, C.POINTER(PbParams)]),
 }

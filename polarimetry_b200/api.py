@@ -413,6 +413,33 @@ class Engine:
                                            int(bin[0]), int(bin[1]), out.data_ptr(), self._stream()), 'pb_get_intensity')
         return out
 
+    def compute_dark(self, values, size_cell: int = 20) -> float:
+        """Stack.compute_dark (PC:266-278) on the device (integer stacks)."""
+        t = self._to_device(values)
+        N, H, W = t.shape
+        out = C.c_double(0.0)
+        self._ck(self.lib.pb_compute_dark(self._ctx, t.data_ptr(), _cabi.DTYPES[self._dtype_name(t)], N, H, W, int(size_cell),
+                                          C.byref(out), self._stream()), 'pb_compute_dark')
+        return float(out.value)
+
+    def calibration_sweep(self, stacks: Sequence, disks: Sequence['Calibration'], p: AnalysisParams, rois: Optional[Sequence[dict]] = None,
+                          per_roi: bool = False, base_mask=None) -> List[dict]:
+        """The 1PF calibration sweep (PP:850-913, "next" row N1): every disk cone against every stack, one statistics row per
+        (disk, stack, ROI) as `analyze_stack(for_calib=True)` returns them (numeric columns of return_vecexcel, PP:2739-2779).
+        The stacks stay resident on the device; only the LUT changes between disks."""
+        dev_stacks = [self._to_device(s) for s in stacks]
+        rows = []
+        for d, cal in enumerate(disks):
+            for k, st in enumerate(dev_stacks):
+                res = self.analyze(st, p, cal, rois, per_roi, base_mask, want_hist=False)
+                sel_rois = [r for r in (rois or []) if r.get('select')] if per_roi else []
+                targets = [(r['indx'], g) for g, r in enumerate(sel_rois)] or [(None, 0)]
+                for idx, g in targets:
+                    row = self.roi_stats(res, p, idx, g)
+                    row.update(disk=cal.name or d, stack=k, roi=idx if idx is not None else 1)
+                    rows.append(row)
+        return rows
+
     def field(self, values, p: AnalysisParams) -> torch.Tensor:
         """analyze_stack's pre-processing + binning (PP:2953-2962) -> double field [N,H,W]."""
         t = self._to_device(values)

@@ -23,6 +23,10 @@ cudaError_t pb_launch_stats(int pass, const void *vals, const void *rho, int is_
                             double rot_fig, int rewrap, int fold90, double mean, double *acc, cudaStream_t st);
 cudaError_t pb_launch_fit_maps(const double *f, const uint8_t *mask, long long P, int N, int nharm, const Basis2 &bs, double *fit,
                                double *chi2, cudaStream_t st);
+cudaError_t pb_launch_dark_cells(const void *plane0, int dtype, int W, int ny, int nx, int cell, unsigned long long *sums, unsigned *counts,
+                                 cudaStream_t st);
+cudaError_t pb_launch_dark_cell_all(const void *stack, int dtype, long long P, int W, int N, int y0, int x0, int cell,
+                                    unsigned long long *out, cudaStream_t st);
 bool pb_march_supported(const pb_params *p);
 cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches);
 
@@ -508,6 +512,47 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     double var = acc[4] / cnt - md * md;
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
+    return ws_release(ctx, st);
+}
+
+int pb_compute_dark(pb_ctx *ctx, const void *stack, int dtype, int N, int H, int W, int size_cell, double *dark_host, void *stream) {
+    if (!ctx || !stack || !dark_host || size_cell < 1) return fail(ctx, PB_ERR_ARG, "pb_compute_dark: bad argument");
+    if (dtype != PB_U8 && dtype != PB_U16) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_compute_dark: integer stacks only (uint8 / uint16)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ny = H / size_cell, nx = W / size_cell;
+    *dark_host = 0.0;
+    if (N < 1 || ny < 1 || nx < 1) return PB_OK;                        // values.size == 0 -> 0.0 (PC:267-268)
+    const size_t ncell = (size_t)ny * nx;
+    int rc;
+    if ((rc = ws_reserve(ctx, 4, ncell * 12 + 64))) return rc;
+    if ((rc = ws_acquire(ctx, st))) return rc;
+    unsigned long long *sums = (unsigned long long *)ctx->ws[4];
+    unsigned *counts = (unsigned *)(sums + ncell + 2);
+    CK(pb_launch_dark_cells(stack, dtype, W, ny, nx, size_cell, sums, counts, st)); ctx->launches++;
+    std::vector<unsigned long long> hs(ncell);
+    std::vector<unsigned> hc(ncell);
+    CK(cudaMemcpyAsync(hs.data(), sums, ncell * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc.data(), counts, ncell * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // np.argmin of the masked means: cells without a non-zero sample are masked (filled with the maximum) -> first minimum
+    size_t best = 0;
+    double bestv = INFINITY;
+    bool any = false;
+    for (size_t k = 0; k < ncell; ++k) {
+        if (!hc[k]) continue;
+        const double m = (double)hs[k] / (double)hc[k];
+        if (!any || m < bestv) { bestv = m; best = k; any = true; }
+    }
+    if (!any) best = 0;
+    const int ci = (int)(best / nx), cj = (int)(best % nx);
+    unsigned long long *acc = sums + ncell;
+    CK(cudaMemsetAsync(acc, 0, 16, st));
+    CK(pb_launch_dark_cell_all(stack, dtype, (long long)H * W, W, N, ci * size_cell, cj * size_cell, size_cell, acc, st)); ctx->launches++;
+    unsigned long long r[2];
+    CK(cudaMemcpyAsync(r, acc, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *dark_host = r[1] ? (double)r[0] / (double)r[1] : NAN;              // an all-zero cell has a fully masked mean
     return ws_release(ctx, st);
 }
 

@@ -120,7 +120,59 @@ __global__ void __launch_bounds__(256) k_fit_maps(const double *__restrict__ f, 
     if (chi2o) chi2o[p] = m ? acc / dN : pb_nan();
 }
 
+// Stack.compute_dark (PC:266-278), step 1: per size x size cell of the FIRST angle plane, the sum and the count of the
+// non-zero samples (numpy.ma.masked_equal(.., 0).mean is sum / count, both exact integers). One warp per cell.
+template <typename T>
+__global__ void __launch_bounds__(256) k_dark_cells(const T *__restrict__ plane0, int W, int ny, int nx, int cell,
+                                                    unsigned long long *__restrict__ sums, unsigned *__restrict__ counts) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= ny * nx) return;
+    const int ci = warp / nx, cj = warp - ci * nx;
+    unsigned long long s = 0ull;
+    unsigned c = 0u;
+    for (int e = lane; e < cell * cell; e += 32) {
+        const int dy = e / cell, dx = e - dy * cell;
+        const unsigned v = (unsigned)plane0[(long long)(ci * cell + dy) * W + cj * cell + dx];
+        s += v; c += v != 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); c += __shfl_down_sync(0xffffffffu, c, o); }
+    if (lane == 0) { sums[warp] = s; counts[warp] = c; }
+}
+
+// step 2: the same sum / count over ALL angle planes of the chosen cell (PC:276-278)
+template <typename T>
+__global__ void __launch_bounds__(256) k_dark_cell_all(const T *__restrict__ stack, long long P, int W, int N, int y0, int x0, int cell,
+                                                       unsigned long long *__restrict__ out /* [0]=sum, [1]=count */) {
+    unsigned long long s = 0ull, c = 0ull;
+    const int per = cell * cell, total = per * N;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int i = e / per, r = e - i * per, dy = r / cell, dx = r - dy * cell;
+        const unsigned v = (unsigned)stack[(long long)i * P + (long long)(y0 + dy) * W + x0 + dx];
+        s += v; c += v != 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); c += __shfl_down_sync(0xffffffffu, c, o); }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, s); atomicAdd(out + 1, c); }
+}
+
 }  // namespace
+
+cudaError_t pb_launch_dark_cells(const void *plane0, int dtype, int W, int ny, int nx, int cell, unsigned long long *sums, unsigned *counts,
+                                 cudaStream_t st) {
+    const int warps = ny * nx, blocks = (warps * 32 + 255) / 256;
+    if (dtype == PB_U8) k_dark_cells<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)plane0, W, ny, nx, cell, sums, counts);
+    else if (dtype == PB_U16) k_dark_cells<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t *)plane0, W, ny, nx, cell, sums, counts);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t pb_launch_dark_cell_all(const void *stack, int dtype, long long P, int W, int N, int y0, int x0, int cell,
+                                    unsigned long long *out, cudaStream_t st) {
+    const int blocks = (cell * cell * N + 255) / 256 < 64 ? (cell * cell * N + 255) / 256 : 64;
+    if (dtype == PB_U8) k_dark_cell_all<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t *)stack, P, W, N, y0, x0, cell, out);
+    else if (dtype == PB_U16) k_dark_cell_all<uint16_t><<<blocks, 256, 0, st>>>((const uint16_t *)stack, P, W, N, y0, x0, cell, out);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
 
 cudaError_t pb_launch_histo(const void *vals, int is_f64, const uint8_t *sel, long long n, int is_rho, double rot_fig, int fold90,
                             const double *edges_dev, int nbins, double inv_w, int64_t *counts, cudaStream_t st) {

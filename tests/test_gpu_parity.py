@@ -224,3 +224,34 @@ def test_larger_stack_properties(eng):
         rho = a.vars[0].values
         assert int(a.hist[('Rho', None)].sum()) == int(torch.isfinite(rho).sum())
         assert 0 < int(a.mask.sum()) < v.shape[1] * v.shape[2]
+
+
+def test_compute_dark_on_device(eng):
+    """"next" row N2: Stack.compute_dark (PC:266-278), exact integer sums on the device."""
+    from polarimetry_b200 import synth
+    for seed, shape, dt in ((1, (18, 100, 130), np.uint16), (2, (4, 64, 64), np.uint16), (3, (6, 41, 59), np.uint8), (4, (18, 512, 512), np.uint16)):
+        v = synth.stack_1pf(shape[1], shape[2], shape[0], seed, dtype=dt, level=2000.0 if dt == np.uint16 else 100.0,
+                            amp=1500.0 if dt == np.uint16 else 60.0, dark=480 if dt == np.uint16 else 0)
+        v[:, :25, :25] = np.minimum(v[:, :25, :25], 60)
+        v[0, 3:9, 4:11] = 0
+        assert eng.compute_dark(v) == rs.compute_dark(v), shape
+    assert eng.compute_dark(np.zeros((3, 10, 10), dtype=np.uint16)) == 0.0     # smaller than one cell -> 0.0 like an empty stack
+
+
+def test_calibration_sweep(eng):
+    """"next" row N1: disks x stacks sweep (PP:883-898), statistics rows against the oracle at the reference's 3 decimals."""
+    from polarimetry_b200 import synth
+    stacks = [synth.stack_1pf(48, 64, 18, seed=200 + k) for k in range(2)]
+    names = [cases.DISK_NODIST, cases.DISK_561]
+    disks = [Calibration(util.load_disk(n).rho_table, util.load_disk(n).psi_table, 401, name=n) for n in names]
+    p = AnalysisParams(method='1PF', dark=480.0, bins=(2, 2), ilow=30000.0, offset_angle=60.0)
+    rows = eng.calibration_sweep(stacks, disks, p)
+    assert len(rows) == 4
+    for row in rows:
+        d = names.index(row['disk'])
+        ref = rs.analyze_stack(stacks[row['stack']], rs.Params(method='1PF', dark=480.0, bins=(2, 2), ilow=30000.0, offset_angle=60.0),
+                               util.load_disk(names[d]))
+        st = ref['stats'][None]
+        assert row['N'] == st['N']
+        for k in ('MeanRho', 'StdRho', 'MeanPsi', 'StdPsi', 'MeanInt', 'StdInt'):
+            assert rs.fmt3(float(row[k])) == rs.fmt3(float(st[k])), (k, row[k], st[k])

@@ -46,3 +46,15 @@ def test_4polar_live(method):
     mine = rs.analyze_stack(v, rs.Params(method=method, dark=0.0, bins=(2, 2)), rs.Calib.from_K(util.load_K(nm)))
     for k in ref['vars']:
         assert util.eq(ref['vars'][k], mine['vars'][k])
+
+
+def test_compute_dark_live():
+    pp, pc = rl.load()
+    from pathlib import Path
+    for seed, shape in ((1, (18, 100, 130)), (2, (4, 64, 64)), (3, (6, 41, 59))):
+        v = synth.stack_1pf(shape[1], shape[2], shape[0], seed)
+        v[:, :25, :25] = np.minimum(v[:, :25, :25], 600)      # a dark corner
+        v[0, 3:9, 4:11] = 0                                    # zeros are masked out
+        st = pc.Stack(Path('/tmp/x.tif'))
+        st.values, (st.nangle, st.height, st.width) = v, v.shape
+        assert rs.compute_dark(v) == st.compute_dark()
