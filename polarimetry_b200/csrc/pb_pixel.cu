@@ -331,16 +331,18 @@ cudaError_t launch_harm_t(const PixArgs &a, const typename BasisSel<NH>::type &b
                       a.sub >= 0 && a.sub <= 65536.0 && a.dark >= 0 && a.dark <= 65536.0;
     const long long nthr = vec ? a.P / 4 : a.P;
     dim3 grid((unsigned)((nthr + threads - 1) / threads), n_stacks);
-    if constexpr (is_int) {
-        if (fast) {
-            if (vec) k_pixel_harm<T, NH, 4, 1><<<grid, threads, smem, st>>>(a, bs);
-            else k_pixel_harm<T, NH, 1, 1><<<grid, threads, smem, st>>>(a, bs);
-            return cudaGetLastError();
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {      // many ROI groups x bins: opt in to a large dynamic shared memory area
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
         }
+        kern<<<grid, threads, smem, st>>>(a, bs);
+        return cudaGetLastError();
+    };
+    if constexpr (is_int) {
+        if (fast) return vec ? launch(k_pixel_harm<T, NH, 4, 1>) : launch(k_pixel_harm<T, NH, 1, 1>);
     }
-    if (vec) k_pixel_harm<T, NH, 4, 0><<<grid, threads, smem, st>>>(a, bs);
-    else k_pixel_harm<T, NH, 1, 0><<<grid, threads, smem, st>>>(a, bs);
-    return cudaGetLastError();
+    return vec ? launch(k_pixel_harm<T, NH, 4, 0>) : launch(k_pixel_harm<T, NH, 1, 0>);
 }
 
 }  // namespace
@@ -370,12 +372,19 @@ cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cu
     size_t smem = pb_hist_smem_bytes(a.n_vars, a.nbins, a.n_groups);
     const int threads = 256;
     dim3 grid((unsigned)((a.P + threads - 1) / threads), n_stacks);
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, threads, smem, st>>>(a);
+        return cudaGetLastError();
+    };
     switch (dtype) {
-    case PB_U8: k_pixel_4polar<uint8_t><<<grid, threads, smem, st>>>(a); break;
-    case PB_U16: k_pixel_4polar<uint16_t><<<grid, threads, smem, st>>>(a); break;
-    case PB_F32: k_pixel_4polar<float><<<grid, threads, smem, st>>>(a); break;
-    case PB_F64: k_pixel_4polar<double><<<grid, threads, smem, st>>>(a); break;
-    default: return cudaErrorInvalidValue;
+    case PB_U8: return launch(k_pixel_4polar<uint8_t>);
+    case PB_U16: return launch(k_pixel_4polar<uint16_t>);
+    case PB_F32: return launch(k_pixel_4polar<float>);
+    case PB_F64: return launch(k_pixel_4polar<double>);
     }
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }

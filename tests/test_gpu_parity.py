@@ -255,3 +255,63 @@ def test_calibration_sweep(eng):
         assert row['N'] == st['N']
         for k in ('MeanRho', 'StdRho', 'MeanPsi', 'StdPsi', 'MeanInt', 'StdInt'):
             assert rs.fmt3(float(row[k])) == rs.fmt3(float(st[k])), (k, row[k], st[k])
+
+
+def test_full_width_stack_against_oracle(eng):
+    """1024x1024x18 (BASELINE configs[0] shape), bin 3x3 and 1x1, straight against the oracle: every map and bin exact."""
+    from polarimetry_b200 import synth
+    v = synth.stack_1pf(1024, 1024, 18, seed=11)
+    cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
+    ocal = util.load_disk(cases.DISK_NODIST)
+    for bins in ((3, 3), (1, 1)):
+        res = eng.analyze(v, AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=45000.0), cal)
+        ref = rs.analyze_stack(v, rs.Params(method='1PF', dark=480.0, bins=bins, ilow=45000.0), ocal)
+        assert res.plan == ('fused_march' if bins[0] > 1 else 'fused_pixel')
+        for var in res.vars:
+            assert util.eq(var.values.cpu().numpy(), ref['vars'][var.name]), (bins, var.name)
+        assert util.eq(res.mask.cpu().numpy().astype(bool), ref['mask'])
+        assert util.eq(res.intmap.cpu().numpy(), ref['intmap'])
+        for k, h in res.hist.items():
+            assert util.eq(h, ref['hist'][k]), (bins, k)
+
+
+def test_many_rois_and_bins(eng):
+    """32 ROIs, per-ROI histograms with 128 bins: the per-CTA histogram area exceeds 48 KB of shared memory."""
+    c = util.CASE_BY_NAME['shg_bin1']
+    g = util.golden('shg_bin1')
+    v = g['values']
+    H, W = v.shape[1:]
+    rois = [dict(indx=k + 1, vertices=np.array([[2.0 + k, 50.0, 50.0, 2.0 + k], [1.0, 1.0, 38.0 - (k % 7), 38.0]]), ILow='0', select=True)
+            for k in range(32)]
+    p = util.params_for(c)
+    p.nbins = 128
+    ref = rs.analyze_stack(v, p, None, rois, True)
+    res = eng.analyze(v, params_for(c, ), None, rois, True) if False else eng.analyze(v, AnalysisParams(method='SHG', dark=0.0, nbins=128), None, rois, True)
+    assert len(res.hist) == 32 * 4
+    for k, h in res.hist.items():
+        assert util.eq(h, ref['hist'][k]), k
+
+
+def test_error_paths_return_codes(eng):
+    """Bad calls fail with a negative status and a message; nothing falls back."""
+    import ctypes as C
+    from polarimetry_b200 import _cabi
+    lib, ctx = eng.lib, eng._ctx
+    # establish the context state (basis for N = 18, a disk cone) with one valid call
+    eng.analyze(np.full((18, 8, 8), 1000, dtype=np.uint16), AnalysisParams(method='1PF'), calib_for(util.CASE_BY_NAME['1pf_bin1x1']))
+    p = _cabi.PbParams(0, 1, 18, 8, 8, 1, 1, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 500.0, 0.0)
+    o = _cabi.PbOutputs()
+    assert lib.pb_analyze(ctx, C.byref(p), None, 1, None, None, C.byref(o), None) == -1          # NULL stack
+    assert b'NULL' in lib.pb_last_error(ctx)
+    p.method = 9
+    assert lib.pb_analyze(ctx, C.byref(p), C.c_void_p(8), 1, None, None, C.byref(o), None) == -1   # unknown method
+    p.method, p.N = 5, 18
+    assert lib.pb_analyze(ctx, C.byref(p), C.c_void_p(8), 1, None, None, C.byref(o), None) == -1   # 4POLAR needs 4 planes
+    p.method, p.N = 0, 12
+    assert lib.pb_analyze(ctx, C.byref(p), C.c_void_p(8), 1, None, None, C.byref(o), None) == -3   # basis not set for this N
+    p.method, p.N, p.bin_h = 0, 18, 40
+    assert lib.pb_analyze(ctx, C.byref(p), C.c_void_p(8), 1, None, None, C.byref(o), None) == -4   # unsupported window
+    with pytest.raises(ValueError):
+        eng.analyze(np.zeros((18, 8, 8), dtype=np.uint16), AnalysisParams(method='1PF'), None)     # 1PF without a disk cone
+    with pytest.raises(TypeError):
+        eng.analyze(np.zeros((18, 8, 8), dtype=np.int64), AnalysisParams(method='SHG'))            # unsupported dtype
