@@ -175,54 +175,60 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
             const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
             const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
             // ---- phase A: the (plane, row) lines advance XT extended positions
+            // one step of a line: q = RN(S1 / bh) [(double)S1 = (2^52 + S1) - 2^52 exactly; H pass skipped if bh <= 1, PP:2944],
+            // tmp += q - ring (W pass, skipped if BW == 1), f = RN(tmp / bw)
+            auto line_step = [&](int c, int j, int S1) -> double {
+                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+                const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+                if constexpr (BW == 1) {
+                    return q;
+                } else {
+                    const double old = ring[c][j % BW];
+                    ring[c][j % BW] = q;
+                    tmp[c] = tmp[c] + (q - old);
+                    return fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+                }
+            };
+            if (plane0 + PL <= N) {
+                // all PL lines of this thread are image planes: interleave them position by position so that their
+                // (independent) running-sum dependency chains overlap
+                const uint16_t *rp = rawb + plane0 * plane_pitch + lane * RP;
 #pragma unroll
-            for (int c = 0; c < PL; ++c) {
-                const int plane = plane0 + c;
-                double *fo = cfo + c * (MR * FP);
-                if (plane < N) {
-                    const uint16_t *rp = rawb + plane * plane_pitch + lane * RP;
+                for (int j = 0; j < XT; ++j) {
 #pragma unroll
-                    for (int j = 0; j < XT; ++j) {
+                    for (int c = 0; c < PL; ++c) {
                         int S1 = 0;
                         if constexpr (SQ) {
 #pragma unroll
-                            for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[dy * RP + j];
+                            for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
                         } else {
-                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP + j];
+                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
                         }
-                        // (double)S1 exactly: (2^52 + S1) - 2^52 ; then RN(S1 / bh) unless the H pass is skipped (bh <= 1, PP:2944)
-                        const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-                        const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-                        double f;
-                        if constexpr (BW == 1) {
-                            f = q;                                   // W pass skipped (size <= 1)
-                        } else {
-                            const double old = ring[c][j % BW];
-                            ring[c][j % BW] = q;
-                            tmp[c] = tmp[c] + (q - old);
-                            f = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);   // RN(tmp / bw)
-                        }
-                        fo[j] = f;
+                        cfo[c * (MR * FP) + j] = line_step(c, j, S1);
                     }
-                } else if (plane == N) {
-                    // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
-                    const int *tp = Tb + lane * XT;
+                }
+            } else {
 #pragma unroll
-                    for (int j = 0; j < XT; ++j) {
-                        int S1 = 0;
-                        for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT + j];
-                        const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-                        const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-                        double f;
-                        if constexpr (BW == 1) {
-                            f = q;
-                        } else {
-                            const double old = ring[c][j % BW];
-                            ring[c][j % BW] = q;
-                            tmp[c] = tmp[c] + (q - old);
-                            f = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+                for (int c = 0; c < PL; ++c) {
+                    const int plane = plane0 + c;
+                    double *fo = cfo + c * (MR * FP);
+                    if (plane < N) {
+                        const uint16_t *rp = rawb + plane * plane_pitch + lane * RP;
+#pragma unroll
+                        for (int j = 0; j < XT; ++j) {
+                            int S1 = 0;
+                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP + j];
+                            fo[j] = line_step(c, j, S1);
                         }
-                        fo[j] = f;
+                    } else if (plane == N) {
+                        // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
+                        const int *tp = Tb + lane * XT;
+#pragma unroll
+                        for (int j = 0; j < XT; ++j) {
+                            int S1 = 0;
+                            for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT + j];
+                            fo[j] = line_step(c, j, S1);
+                        }
                     }
                 }
             }
