@@ -63,12 +63,15 @@ __device__ __forceinline__ double pb_nan() { return __longlong_as_double(0x7ff80
 __device__ __forceinline__ double pb_max0(double x) { return (x > 0.0) ? x : ((x != x) ? x : 0.0); }
 
 // np.mod(a, b) for b > 0: python-sign modulo; a tiny negative a gives exactly b
-__device__ __forceinline__ double pb_pymod(double a, double b) {
-    if (a > 0.0 && a < b) return a;               // fmod(a,b) == a
+static __device__ __noinline__ double pb_pymod_general(double a, double b) {
     double r = fmod(a, b);
     if (r != 0.0) { if (r < 0.0) r = r + b; }
     else r = 0.0;
     return r;
+}
+__device__ __forceinline__ double pb_pymod(double a, double b) {
+    if (a > 0.0 && a < b) return a;               // fmod(a,b) == a: the common case, kept inline
+    return pb_pymod_general(a, b);
 }
 
 template <typename T> __device__ __forceinline__ double pb_to_double(T v) { return (double)v; }

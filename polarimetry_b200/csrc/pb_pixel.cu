@@ -187,25 +187,55 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
             Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
             in[k].S0 = S0d[k]; in[k].Sc = Sc[k]; in[k].Ss = Ss[k]; in[k].Sc4 = Sc4[k]; in[k].Ss4 = Ss4[k]; in[k].Sff = Sffd[k]; in[k].I = Iv[k];
         }
-#pragma unroll(NH == 1 ? PX : 1)
-        for (int k = 0; k < PX; ++k) {
-            const PixIn x = in[k];
-            HarmPix hp = harm_stage_a<NH>(a, p0 + k, x.S0, x.Sc, x.Ss, x.Sc4, x.Ss4, x.Sff, x.I);
-            if (hp.need) {
-                // rare path: the reference's fp64 fit/chi2 loop for an undecided pixel (stack re-read, L1/L2 hits)
-                ExactAcc ex;
-                ex.init();
-                const T *px = base + k;
-                for (int i = 0; i < N; ++i) {
-                    double f = (double)__ldg(px + (long long)i * P);
-                    if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
-                    double c4 = 0.0, s4 = 0.0;
-                    if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-                    ex.template step<NH>(hp, f, bs.c2[i], bs.s2[i], c4, s4);
-                }
-                hp.m = ex.decide(a);
+        if constexpr (NH == 1) {
+            HarmPix hp[PX];
+            bool any_need = false;
+#pragma unroll
+            for (int k = 0; k < PX; ++k) {
+                hp[k] = harm_stage_a<NH>(a, p0 + k, in[k].S0, in[k].Sc, in[k].Ss, in[k].Sc4, in[k].Ss4, in[k].Sff, in[k].I);
+                any_need |= hp[k].need;
             }
-            o[k] = harm_stage_b<NH>(a, hs, do_hist, hp);
+            if (any_need) {
+                // rare path: the reference's fp64 fit/chi2 loop for the undecided pixels of this thread (stack re-read, L1/L2 hits)
+                ExactAcc ex[PX];
+#pragma unroll
+                for (int k = 0; k < PX; ++k) ex[k].init();
+                for (int i = 0; i < N; ++i) {
+                    double v[PX];
+                    VecLoad<T, PX>::ld(base + (long long)i * P, v);
+#pragma unroll
+                    for (int k = 0; k < PX; ++k) {
+                        double f = v[k];
+                        if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
+                        ex[k].template step<NH>(hp[k], f, bs.c2[i], bs.s2[i], 0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < PX; ++k)
+                    if (hp[k].need) hp[k].m = ex[k].decide(a);
+            }
+#pragma unroll
+            for (int k = 0; k < PX; ++k) o[k] = harm_stage_b<NH>(a, hs, do_hist, hp[k]);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < PX; ++k) {
+                const PixIn x = in[k];
+                HarmPix hp = harm_stage_a<NH>(a, p0 + k, x.S0, x.Sc, x.Ss, x.Sc4, x.Ss4, x.Sff, x.I);
+                if (hp.need) {
+                    ExactAcc ex;
+                    ex.init();
+                    const T *px = base + k;
+                    for (int i = 0; i < N; ++i) {
+                        double f = (double)__ldg(px + (long long)i * P);
+                        if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
+                        double c4 = 0.0, s4 = 0.0;
+                        if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
+                        ex.template step<NH>(hp, f, bs.c2[i], bs.s2[i], c4, s4);
+                    }
+                    hp.m = ex.decide(a);
+                }
+                o[k] = harm_stage_b<NH>(a, hs, do_hist, hp);
+            }
         }
         if constexpr (PX == 4) {
             store4(out.var[0], p0, o[0].v0, o[1].v0, o[2].v0, o[3].v0, f64);
