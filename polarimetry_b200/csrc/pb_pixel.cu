@@ -77,6 +77,27 @@ __device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigne
     }
 }
 
+// one plane (tail of the angle loop)
+template <typename UT, int NH, int PX, typename Basis>
+__device__ __forceinline__ void compute_one(IntState<UT, PX> &s, const unsigned *w, const Basis &bs, int i, int isub, int idark, bool sep) {
+    const double c2 = bs.c2[i], s2 = bs.s2[i], kc2 = bs.kc2[i], ks2 = bs.ks2[i];
+#pragma unroll
+    for (int k = 0; k < PX; ++k) {
+        const int v = (int)RawLoad<UT, PX>::get(w, k);
+        const int f = max(v - isub, 0);
+        if (sep) s.Ii[k] += (unsigned)max(v - idark, 0);
+        s.S0[k] += (unsigned)f;
+        s.Sff[k] += (unsigned long long)((unsigned)f) * (unsigned)f;
+        const double X = __hiloint2double(0x43300000, f);
+        s.Sc[k] = s.Sc[k] + fma(X, c2, kc2);
+        s.Ss[k] = s.Ss[k] + fma(X, s2, ks2);
+        if constexpr (NH == 2) {
+            s.Sc4[k] = s.Sc4[k] + fma(X, bs.c4[i], bs.kc4[i]);
+            s.Ss4[k] = s.Ss4[k] + fma(X, bs.s4[i], bs.ks4[i]);
+        }
+    }
+}
+
 // vector stores of 4 consecutive pixels
 __device__ __forceinline__ void store4(void *base, long long p, double x0, double x1, double x2, double x3, bool f64) {
     if (!base) return;
@@ -116,22 +137,29 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
 #pragma unroll
             for (int k = 0; k < PX; ++k) { s.Sc[k] = s.Ss[k] = s.Sc4[k] = s.Ss4[k] = 0.0; s.S0[k] = s.Ii[k] = 0u; s.Sff[k] = 0ull; }
             unsigned A[CH][RawLoad<UT, PX>::WORDS], B[CH][RawLoad<UT, PX>::WORDS];
+            // full chunks of CH planes, ping-pong: A holds planes [i, i+CH), B is loaded while A is consumed, and vice versa.
+            // (Only the unpredicated chunk code is instantiated -- twice -- to keep the kernel inside the instruction cache;
+            // the N % CH remaining planes go through a small rolled loop.)
+            const int nfull = N / CH;
             int i = 0;
-            if (N >= CH) load_chunk<UT, PX, true>(ptr, P, A, CH); else load_chunk<UT, PX, false>(ptr, P, A, N);
-            // ping-pong: A holds angles [i, i+nA), B is loaded while A is consumed, and vice versa
-            while (true) {
-                const int nA = min(CH, N - i), nB = min(CH, N - i - nA);
-                if (nB == CH) load_chunk<UT, PX, true>(ptr, P, B, CH); else load_chunk<UT, PX, false>(ptr, P, B, nB);
-                if (nA == CH) compute_chunk<UT, NH, PX, true>(s, A, bs, i, CH, isub, idark, sep);
-                else compute_chunk<UT, NH, PX, false>(s, A, bs, i, nA, isub, idark, sep);
-                i += nA;
-                if (i >= N) break;
-                const int nA2 = min(CH, N - i - nB);
-                if (nA2 == CH) load_chunk<UT, PX, true>(ptr, P, A, CH); else load_chunk<UT, PX, false>(ptr, P, A, nA2);
-                if (nB == CH) compute_chunk<UT, NH, PX, true>(s, B, bs, i, CH, isub, idark, sep);
-                else compute_chunk<UT, NH, PX, false>(s, B, bs, i, nB, isub, idark, sep);
-                i += nB;
-                if (i >= N) break;
+            if (nfull > 0) {
+                load_chunk<UT, PX, true>(ptr, P, A, CH);
+                for (int c = 0; c < nfull; c += 2) {
+                    if (c + 1 < nfull) load_chunk<UT, PX, true>(ptr, P, B, CH);
+                    compute_chunk<UT, NH, PX, true>(s, A, bs, i, CH, isub, idark, sep);
+                    i += CH;
+                    if (c + 1 >= nfull) break;
+                    if (c + 2 < nfull) load_chunk<UT, PX, true>(ptr, P, A, CH);
+                    compute_chunk<UT, NH, PX, true>(s, B, bs, i, CH, isub, idark, sep);
+                    i += CH;
+                }
+            }
+#pragma unroll 1
+            for (; i < N; ++i) {
+                unsigned w[1][RawLoad<UT, PX>::WORDS];
+                RawLoad<UT, PX>::ld(ptr, w[0]);
+                ptr += P;
+                compute_one<UT, NH, PX>(s, w[0], bs, i, isub, idark, sep);
             }
 #pragma unroll
             for (int k = 0; k < PX; ++k) {

@@ -52,6 +52,7 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
     } else if (a.n_groups == 1) {
         if (bits & a.group_bits[0]) atomicAdd(c, 1u);
     } else {
+#pragma unroll 1
         for (int g = 0; g < a.n_groups; ++g)
             if (bits & a.group_bits[g]) atomicAdd(c + g * a.n_vars * nb, 1u);
     }
@@ -61,7 +62,8 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
 __device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double I) {
     if (a.n_rois == 0) return (bits != 0u) && (I >= a.roi_ilow[0]);
     bool ok = false;
-    for (int r = 0; r < a.n_rois; ++r) ok |= ((bits >> r) & 1u) && (I >= a.roi_ilow[r]);
+#pragma unroll 1
+    for (int r = 0; r < a.n_rois; ++r) ok |= ((bits >> r) & 1u) && (I >= a.roi_ilow[r]);   // rolled: keeps the kernels inside the instruction cache
     return ok;
 }
 
