@@ -50,9 +50,9 @@ __device__ __forceinline__ void load_chunk(const UT *&ptr, long long P, unsigned
 // one chunk of the projection on the integer fast path: per pixel-angle one unpack, one fused subtract/clamp,
 // integer S0 and sum f^2, and per harmonic component ONE DFMA (the rounded product RN(f c) = fma(2^52+f, c, -(2^52 c)))
 // plus ONE DADD (the reference's separately rounded accumulation, PP:2989 / einsum).
-template <typename UT, int NH, int PX, bool FULL, typename Basis>
+template <typename UT, int NH, int PX, bool FULL, bool SEP, typename Basis>
 __device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigned (&buf)[CH][RawLoad<UT, PX>::WORDS], const Basis &bs,
-                                              int i0, int cnt, int isub, int idark, bool sep) {
+                                              int i0, int cnt, int isub, int idark) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
         if (FULL || j < cnt) {
@@ -62,7 +62,7 @@ __device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigne
             for (int k = 0; k < PX; ++k) {
                 const int v = (int)RawLoad<UT, PX>::get(buf[j], k);
                 const int f = max(v - isub, 0);
-                if (sep) s.Ii[k] += (unsigned)max(v - idark, 0);
+                if constexpr (SEP) s.Ii[k] += (unsigned)max(v - idark, 0);
                 s.S0[k] += (unsigned)f;
                 s.Sff[k] += (unsigned long long)((unsigned)f) * (unsigned)f;
                 const double X = __hiloint2double(0x43300000, f);   // 2^52 + f, exact
@@ -78,14 +78,14 @@ __device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigne
 }
 
 // one plane (tail of the angle loop)
-template <typename UT, int NH, int PX, typename Basis>
-__device__ __forceinline__ void compute_one(IntState<UT, PX> &s, const unsigned *w, const Basis &bs, int i, int isub, int idark, bool sep) {
+template <typename UT, int NH, int PX, bool SEP, typename Basis>
+__device__ __forceinline__ void compute_one(IntState<UT, PX> &s, const unsigned *w, const Basis &bs, int i, int isub, int idark) {
     const double c2 = bs.c2[i], s2 = bs.s2[i], kc2 = bs.kc2[i], ks2 = bs.ks2[i];
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
         const int v = (int)RawLoad<UT, PX>::get(w, k);
         const int f = max(v - isub, 0);
-        if (sep) s.Ii[k] += (unsigned)max(v - idark, 0);
+        if constexpr (SEP) s.Ii[k] += (unsigned)max(v - idark, 0);
         s.S0[k] += (unsigned)f;
         s.Sff[k] += (unsigned long long)((unsigned)f) * (unsigned)f;
         const double X = __hiloint2double(0x43300000, f);
@@ -113,6 +113,7 @@ __device__ __forceinline__ void store4(void *base, long long p, double x0, doubl
 // Fused per-pixel kernel, harmonic modalities (1PF: NH=1, CARS/SRS/SHG/2PF: NH=2). One thread = PX
 // consecutive pixels; angle planes are streamed CH at a time with the next chunk's loads in flight.
 //   MODE 1: integer fast path -- uint8/uint16 stack, integer-valued dark and dark+removed, no sqrt.
+//   MODE 2: the same with removed_intensity != 0 (the threshold image then needs its own clamp with `dark` alone, PC:261).
 //   MODE 0: generic -- fp64 pre-processing (float input, fractional dark, CARS sqrt, or an already binned double field).
 template <typename T, int NH, int PX, int MODE>
 __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
@@ -128,11 +129,11 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
         const T *base = reinterpret_cast<const T *>(a.stack) + (long long)blockIdx.y * a.stack_stride + p0;
         const int N = a.N;
         double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX], S0d[PX], Sffd[PX], Id[PX];
-        if constexpr (MODE == 1) {
+        if constexpr (MODE >= 1) {
+            constexpr bool SEP = MODE == 2;
             using UT = typename std::conditional<std::is_same<T, uint8_t>::value, uint8_t, uint16_t>::type;
             const UT *ptr = reinterpret_cast<const UT *>(base);
             const int isub = (int)a.sub, idark = (int)a.dark;
-            const bool sep = isub != idark;
             IntState<UT, PX> s;
 #pragma unroll
             for (int k = 0; k < PX; ++k) { s.Sc[k] = s.Ss[k] = s.Sc4[k] = s.Ss4[k] = 0.0; s.S0[k] = s.Ii[k] = 0u; s.Sff[k] = 0ull; }
@@ -146,11 +147,11 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
                 load_chunk<UT, PX, true>(ptr, P, A, CH);
                 for (int c = 0; c < nfull; c += 2) {
                     if (c + 1 < nfull) load_chunk<UT, PX, true>(ptr, P, B, CH);
-                    compute_chunk<UT, NH, PX, true>(s, A, bs, i, CH, isub, idark, sep);
+                    compute_chunk<UT, NH, PX, true, SEP>(s, A, bs, i, CH, isub, idark);
                     i += CH;
                     if (c + 1 >= nfull) break;
                     if (c + 2 < nfull) load_chunk<UT, PX, true>(ptr, P, A, CH);
-                    compute_chunk<UT, NH, PX, true>(s, B, bs, i, CH, isub, idark, sep);
+                    compute_chunk<UT, NH, PX, true, SEP>(s, B, bs, i, CH, isub, idark);
                     i += CH;
                 }
             }
@@ -159,14 +160,14 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
                 unsigned w[1][RawLoad<UT, PX>::WORDS];
                 RawLoad<UT, PX>::ld(ptr, w[0]);
                 ptr += P;
-                compute_one<UT, NH, PX>(s, w[0], bs, i, isub, idark, sep);
+                compute_one<UT, NH, PX, SEP>(s, w[0], bs, i, isub, idark);
             }
 #pragma unroll
             for (int k = 0; k < PX; ++k) {
                 Sc[k] = s.Sc[k]; Ss[k] = s.Ss[k]; Sc4[k] = s.Sc4[k]; Ss4[k] = s.Ss4[k];
                 S0d[k] = (double)s.S0[k];
                 Sffd[k] = (double)s.Sff[k];
-                Id[k] = sep ? (double)s.Ii[k] : S0d[k];
+                Id[k] = SEP ? (double)s.Ii[k] : S0d[k];
             }
         } else {
             const bool pre = !a.from_field;
@@ -398,7 +399,8 @@ cudaError_t launch_harm_t(const PixArgs &a, const typename BasisSel<NH>::type &b
         return cudaGetLastError();
     };
     if constexpr (is_int) {
-        if (fast) return vec ? launch(k_pixel_harm<T, NH, 4, 1>) : launch(k_pixel_harm<T, NH, 1, 1>);
+        if (fast && a.sub == a.dark) return vec ? launch(k_pixel_harm<T, NH, 4, 1>) : launch(k_pixel_harm<T, NH, 1, 1>);
+        if (fast) return vec ? launch(k_pixel_harm<T, NH, 4, 2>) : launch(k_pixel_harm<T, NH, 1, 2>);
     }
     return vec ? launch(k_pixel_harm<T, NH, 4, 0>) : launch(k_pixel_harm<T, NH, 1, 0>);
 }
