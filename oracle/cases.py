@@ -45,6 +45,8 @@ def all_cases():
     c.append(_c('1pf_disk640_bin2', ('1pf', dict(H=H, W=W, N=18, seed=2)), bins=(2, 2), disk=DISK_640, offset_angle=60.0))
     c.append(_c('1pf_ccw_rot', g1, polar_dir='counterclockwise', offset_angle=17.5, rotation=(33.0, 12.0, 0.0), bins=(3, 3)))
     c.append(_c('1pf_removed', g1, removed_intensity=150, bins=(3, 3), ilow=30000.0, nbins=90))
+    c.append(_c('1pf_removed_bin1', g1, removed_intensity=150, ilow=30000.0))
+    c.append(_c('shg_removed_bin1', ('4harm', dict(H=H, W=W, N=36, seed=2, dark=100)), method='SHG', dark=100.0, removed_intensity=40))
     c.append(_c('1pf_n12', ('1pf', dict(H=H, W=W, N=12, seed=3)), bins=(3, 3), nbins=10))
     c.append(_c('1pf_n90_bin5', ('1pf', dict(H=24, W=40, N=90, seed=4)), bins=(5, 5)))
     c.append(_c('1pf_u8', ('1pf', dict(H=H, W=W, N=18, seed=5, dark=0, dtype='uint8', level=100.0, amp=60.0)), dark=0.0, bins=(3, 3)))
