@@ -295,9 +295,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu and a.workload == '1pf':
         workers = host_workers()
-        v, dt = cpu_sample((a.bin, a.bin), workers, per_worker=4)
+        v, dt = cpu_sample((a.bin, a.bin), workers, per_worker=8)
         cpu = {'value': v, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port',
-               'sample': f'{4 * workers} stacks 1024x1024x18 (4 per worker process, {workers} processes) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
+               'sample': f'{8 * workers} stacks 1024x1024x18 (8 per worker process, {workers} processes) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
     if rank == 0:
         line = {'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
