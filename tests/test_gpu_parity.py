@@ -315,3 +315,50 @@ def test_error_paths_return_codes(eng):
         eng.analyze(np.zeros((18, 8, 8), dtype=np.uint16), AnalysisParams(method='1PF'), None)     # 1PF without a disk cone
     with pytest.raises(TypeError):
         eng.analyze(np.zeros((18, 8, 8), dtype=np.int64), AnalysisParams(method='SHG'))            # unsupported dtype
+
+
+def test_drop_in_functions_with_reference_signatures(eng):
+    """The S1-S3 seams exactly as the reference calls them (PP:2968, PP:2962, PP:2245): module-level compute_fields with
+    the reference's positional/keyword arguments and its side effects (mask updated in place, datastack filled),
+    Polarimetry.binning(self, field) reading the spin boxes, Stack.get_intensity(self, dark, bin)."""
+    import types
+    import polarimetry_b200 as pb
+    from polarimetry_b200 import api
+    api._default_engine = eng
+    c = util.CASE_BY_NAME['1pf_noncalib']
+    g = util.golden('1pf_noncalib')
+    v = g['values']
+    p = util.params_for(c)
+    ocal = util.calib_for(c)
+    edge = cases.make_edge(v.shape[1:])
+
+    class Spin:
+        def __init__(self, x): self.x = x
+        def get(self): return self.x
+
+    app = types.SimpleNamespace(bin_spinboxes=[Spin(str(c['bins'][0])), Spin(str(c['bins'][1]))])
+    stack = types.SimpleNamespace(values=v)
+    intensity = pb.get_intensity(stack, dark=c['dark'], bin=[c['bins'][0], c['bins'][1]])
+    assert util.eq(intensity, g['intensity'])
+    field = np.maximum(v - (c['dark'] + 0.0), 0)
+    field = pb.binning(app, field)
+    assert util.eq(field, rs.binning(rs.preprocess(v, p), p.bins))
+    mask = intensity >= c['ilow']
+    calibration = types.SimpleNamespace(RhoPsi=np.moveaxis(np.stack((ocal.rho_table, ocal.psi_table)), 0, -1), xy=(ocal.grid, ocal.grid), name='disk')
+    H, W = v.shape[1:]
+    yy, xx = np.indices((H, W), dtype=float)
+    ds = types.SimpleNamespace(nangle=v.shape[0], height=H, width=W, vars=[], xct=xx.copy(), yct=yy.copy())
+    out = pb.compute_fields(field, ds, mask, method='1PF', polar_dir=c['polar_dir'], offset_angle=c['offset_angle'], calibration=calibration,
+                            edge_contours=edge, reference_angle=c['rotation'][2], rotation=c['rotation'][0], for_calib=False)
+    assert out is ds
+    assert [x.name for x in ds.vars] == util.INDEX['1pf_noncalib']['var_order']
+    for x in ds.vars:
+        assert util.eq(x.values, g['var_' + x.name]), x.name
+    assert util.eq(ds.intmap, g['intmap'])
+    assert util.eq(mask, np.isfinite(g['intmap']))                       # updated in place, as PP:3000 / PP:3025 do
+    assert util.eq(ds.xmap, g['xmap']) and util.eq(ds.ymap, g['ymap'])
+    assert util.eq(np.isnan(ds.chi2), np.isnan(g['chi2']))
+    m = np.isfinite(g['chi2'])
+    assert np.allclose(ds.chi2[m], g['chi2'][m], rtol=1e-12, atol=0)
+    assert np.isnan(ds.field[:, ~mask]).all() and util.eq(ds.field[:, mask], rs.binning(rs.preprocess(v, p), p.bins)[:, mask])
+    api._default_engine = None
