@@ -29,7 +29,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W, N = 2048, 2048, 18
-WORKLOADS = {'1pf': ('1PF', 18), 'shg': ('SHG', 36), '4polar3d': ('4POLAR 3D', 4)}   # BASELINE configs[3] (headline), [1], [2]
+WORKLOADS = {'1pf': ('1PF', 18), 'shg': ('SHG', 36), '4polar3d': ('4POLAR 3D', 4), '1pf90': ('1PF', 90)}   # BASELINE configs[3] (headline), [1], [2]
 DISK = ROOT / 'tests' / 'golden' / 'calib' / 'Disk_Ga0_Pa0_Ta0_Gb0_Pb0_Tb0_Gc0_Pc0_Tc0.npz'
 DARK, ILOW = 480.0, 40000.0
 OUT_BYTES_PER_PIXEL = 13      # rho f32 + psi f32 + intmap f32 + mask u8
@@ -152,7 +152,8 @@ def workload_config(a, batch):
     text = {'1pf': f'1PF batch of {H}x{W}x18 uint16 stacks, dark {DARK:.0f}, bin {a.bin}x{a.bin}, disk-cone LUT (no distortion), '
                    f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
             'shg': f'SHG batch of {H}x{W}x36 uint16 stacks (BASELINE configs[1]), bin {a.bin}x{a.bin}, rho/S2/S4/S_SHG/intensity maps f32 + mask + histograms',
-            '4polar3d': f'4POLAR 3D batch of 4x{H}x{W} uint16 (BASELINE configs[2]), bin {a.bin}x{a.bin}, rho/psi/eta/intensity maps f32 + mask + histograms'}[wl]
+            '4polar3d': f'4POLAR 3D batch of 4x{H}x{W} uint16 (BASELINE configs[2]), bin {a.bin}x{a.bin}, rho/psi/eta/intensity maps f32 + mask + histograms',
+            '1pf90': f'1PF batch of {H}x{W}x90 uint16 stacks (the per-frame shape of BASELINE configs[4] at 1/16 of its field), bin {a.bin}x{a.bin}, maps f32 + mask + histograms'}[wl]
     return {'workload': text, 'ilow': getattr(a, 'ilow', ILOW), 'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
 
 
@@ -190,7 +191,7 @@ def main():
     d = np.load(DISK)
     if method == '1PF':
         cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=a.ilow, out_dtype='float32')
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=a.ilow * N / 18.0, out_dtype='float32')
         gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed)
     elif method == 'SHG':
         cal = None

@@ -28,7 +28,8 @@ void pb_ddrecip(int n, double *hi, double *lo);   // pb_api.cu
 
 namespace {
 
-constexpr int MR = 32;     // rows per CTA (= lanes of a chain warp)
+// MR = rows per CTA is a template parameter: 32 (N + 1 <= 32 lines per row), 16 (<= 64) or 8 (<= 128); a chain warp holds
+// 32/MR groups of MR rows
 constexpr int PL = 2;      // planes (lines) per chain thread
 constexpr int QMAX = 2;    // tile positions per loader thread
 constexpr int LA = 6;      // angle planes per loader batch
@@ -48,8 +49,9 @@ template <int BW> struct StepWidth { static constexpr int M = (8 + BW - 1) / BW;
 template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr int XT = 8; };
 
 // SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
-template <typename UT, int NH, int BW, bool SQ>
+template <typename UT, int NH, int BW, bool SQ, int MR>
 __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
+    constexpr int SUBS = 32 / MR;                       // line groups per chain warp
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
     constexpr int RW = ((XT + 1) / 2) | 1;              // raw tile row pitch in 32-bit words (odd: conflict-free chain loads)
@@ -155,7 +157,8 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
     } else {
         // =========================== compute warps ===========================
         double *fbuf = reinterpret_cast<double *>(smem + ma.off_f);           // [N+1][MR][FP]
-        const int plane0 = warp * PL;                                          // chains (plane0 .. plane0+PL-1, row y0 + lane)
+        const int crow = lane % MR;                                            // chains (plane0 .. plane0+PL-1, row y0 + crow)
+        const int plane0 = (warp * SUBS + lane / MR) * PL;
         // chain state: running sum and the last BW first-pass outputs. The ring starts at 0.0 so that the first BW steps
         // compute tmp + (q - 0.0) = tmp + q, i.e. scipy's left-to-right initial window sum, with the same instruction.
         double tmp[PL], ring[PL][BW];
@@ -165,7 +168,7 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
 #pragma unroll
             for (int s = 0; s < BW; ++s) ring[c][s] = 0.0;
         }
-        double *const cfo = fbuf + (plane0 * MR + lane) * FP;
+        double *const cfo = fbuf + (plane0 * MR + crow) * FP;
         const int pr = tid / XT, pj = tid - pr * XT;                           // pixel role
         const bool pix = tid < MR * XT && (y0 + pr) < H;
         const double *const pfp = fbuf + pr * FP + pj;
@@ -192,7 +195,7 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
             if (plane0 + PL <= N) {
                 // all PL lines of this thread are image planes: interleave them position by position so that their
                 // (independent) running-sum dependency chains overlap
-                const uint16_t *rp = rawb + plane0 * plane_pitch + lane * RP;
+                const uint16_t *rp = rawb + plane0 * plane_pitch + crow * RP;
 #pragma unroll
                 for (int j = 0; j < XT; ++j) {
 #pragma unroll
@@ -213,7 +216,7 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                     const int plane = plane0 + c;
                     double *fo = cfo + c * (MR * FP);
                     if (plane < N) {
-                        const uint16_t *rp = rawb + plane * plane_pitch + lane * RP;
+                        const uint16_t *rp = rawb + plane * plane_pitch + crow * RP;
 #pragma unroll
                         for (int j = 0; j < XT; ++j) {
                             int S1 = 0;
@@ -222,7 +225,7 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                         }
                     } else if (plane == N) {
                         // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
-                        const int *tp = Tb + lane * XT;
+                        const int *tp = Tb + crow * XT;
 #pragma unroll
                         for (int j = 0; j < XT; ++j) {
                             int S1 = 0;
@@ -289,11 +292,12 @@ size_t hist_bytes(const PixArgs &a) {
     return (b + 15) & ~(size_t)15;
 }
 
-template <typename UT, int NH, int BW>
+template <typename UT, int NH, int BW, int MR>
 cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;
     constexpr int RP = 2 * (((XT + 1) / 2) | 1);
+    constexpr int SUBS = 32 / MR;
     MarchArgs ma;
     const int bh = p->bin_h > 1 ? p->bin_h : 1;
     ma.bh = bh; ma.hh = bh / 2; ma.hw = BW / 2;
@@ -301,12 +305,13 @@ cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, c
     ma.tile_rows = MR + bh - 1;
     ma.isub = (int)a.sub; ma.idark = (int)a.dark;
     const int npos = ma.tile_rows * XT;
-    ma.cw = (a.N + 1 + PL - 1) / PL;
+    const int groups = (a.N + 1 + PL - 1) / PL;             // PL lines per chain thread
+    ma.cw = (groups + SUBS - 1) / SUBS;
     if (ma.cw * 32 < MR * XT) ma.cw = (MR * XT + 31) / 32;
     ma.lw = (npos + 32 * QMAX - 1) / (32 * QMAX);
     if (ma.lw < 2 && npos > 32 * 3) ma.lw = 2;
     const int threads = 32 * (ma.cw + ma.lw);
-    if (threads > 1024 || (long long)a.N * a.P >= 2147483647LL) return cudaErrorInvalidConfiguration;
+    if (threads > 1024 || a.P >= 2147483647LL) return cudaErrorInvalidConfiguration;
     pb_ddrecip(bh, &ma.bh_hi, &ma.bh_lo);
     pb_ddrecip(BW, &ma.bw_hi, &ma.bw_lo);
     size_t off = hist_bytes(a);
@@ -319,29 +324,47 @@ cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, c
     dim3 grid((a.H + MR - 1) / MR, n_stacks);
     cudaError_t e;
     if (bh == BW && BW > 1) {
-        auto kern = k_march<UT, NH, BW, true>;
+        auto kern = k_march<UT, NH, BW, true, MR>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
         kern<<<grid, threads, off, st>>>(a, bs, ma);
     } else {
-        auto kern = k_march<UT, NH, BW, false>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
-        kern<<<grid, threads, off, st>>>(a, bs, ma);
+        if constexpr (MR == 32) {
+            auto kern = k_march<UT, NH, BW, false, MR>;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
+            kern<<<grid, threads, off, st>>>(a, bs, ma);
+        } else {
+            return cudaErrorInvalidConfiguration;       // rectangular windows with more than 31 angles: unfused kernels
+        }
     }
     return cudaGetLastError();
 }
 
-template <typename UT, int NH>
-cudaError_t launch_nh(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
+template <typename UT, int NH, int MR>
+cudaError_t launch_mr(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
     const int bw = p->bin_w > 1 ? p->bin_w : 1;
     switch (bw) {
-    case 1: return launch_bw<UT, NH, 1>(a, bs, p, n_stacks, st);
-    case 2: return launch_bw<UT, NH, 2>(a, bs, p, n_stacks, st);
-    case 3: return launch_bw<UT, NH, 3>(a, bs, p, n_stacks, st);
-    case 4: return launch_bw<UT, NH, 4>(a, bs, p, n_stacks, st);
-    case 5: return launch_bw<UT, NH, 5>(a, bs, p, n_stacks, st);
-    case 6: return launch_bw<UT, NH, 6>(a, bs, p, n_stacks, st);
-    case 7: return launch_bw<UT, NH, 7>(a, bs, p, n_stacks, st);
-    case 8: return launch_bw<UT, NH, 8>(a, bs, p, n_stacks, st);
+    case 1: if constexpr (MR == 32) return launch_bw<UT, NH, 1, MR>(a, bs, p, n_stacks, st); else return cudaErrorInvalidConfiguration;
+    case 2: return launch_bw<UT, NH, 2, MR>(a, bs, p, n_stacks, st);
+    case 3: return launch_bw<UT, NH, 3, MR>(a, bs, p, n_stacks, st);
+    case 4: return launch_bw<UT, NH, 4, MR>(a, bs, p, n_stacks, st);
+    case 5: return launch_bw<UT, NH, 5, MR>(a, bs, p, n_stacks, st);
+    case 6: return launch_bw<UT, NH, 6, MR>(a, bs, p, n_stacks, st);
+    case 7: return launch_bw<UT, NH, 7, MR>(a, bs, p, n_stacks, st);
+    case 8: return launch_bw<UT, NH, 8, MR>(a, bs, p, n_stacks, st);
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+// rows per CTA from the number of lines per row (N planes + the intensity plane)
+int march_rows(int N) { return N + 1 <= 32 ? 32 : (N + 1 <= 64 ? 16 : 8); }
+
+template <typename UT, int NH>
+cudaError_t launch_nh(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
+    const int mr = march_rows(a.N);
+    if (mr == 32) return launch_mr<UT, NH, 32>(a, bs, p, n_stacks, st);
+    if constexpr (std::is_same<UT, uint16_t>::value) {      // the many-angle variants are built for uint16 stacks only
+        if (mr == 16) return launch_mr<UT, NH, 16>(a, bs, p, n_stacks, st);
+        return launch_mr<UT, NH, 8>(a, bs, p, n_stacks, st);
     }
     return cudaErrorInvalidConfiguration;
 }
@@ -357,18 +380,21 @@ bool pb_march_supported(const pb_params *p) {
     const double sub = p->dark + p->removed_intensity;
     if (sub != floor(sub) || p->dark != floor(p->dark) || sub < 0 || sub > 65535.0 || p->dark < 0 || p->dark > 65535.0) return false;
     if (p->bin_w > 8 || p->bin_h > 32) return false;
-    if (p->N + 1 > 32 || p->N < 1) return false;
-    if ((long long)p->N * p->H * p->W >= 2147483647LL) return false;      // 32-bit element offsets in the loader
+    if (p->N + 1 > 128 || p->N < 1) return false;
+    if ((long long)p->H * p->W >= 2147483647LL) return false;             // 32-bit in-plane offsets in the loader
     const int bh = p->bin_h > 1 ? p->bin_h : 1, bw = p->bin_w > 1 ? p->bin_w : 1;
+    const int mr = march_rows(p->N);
+    if (mr != 32 && (p->dtype != PB_U16 || bh != bw || bw < 2)) return false;   // many angles: uint16, square windows
     const int xt = bw == 1 ? 8 : bw * ((8 + bw - 1) / bw);
-    int cw = (p->N + 1 + PL - 1) / PL;
-    if (cw * 32 < MR * xt) cw = (MR * xt + 31) / 32;
-    const int npos = (MR + bh - 1) * xt;
+    const int subs = 32 / mr;
+    int cw = (((p->N + 1 + PL - 1) / PL) + subs - 1) / subs;
+    if (cw * 32 < mr * xt) cw = (mr * xt + 31) / 32;
+    const int npos = (mr + bh - 1) * xt;
     int lw = (npos + 32 * QMAX - 1) / (32 * QMAX);
     if (lw < 2) lw = 2;
     if (32 * (cw + lw) > 1024) return false;
     const int rp = 2 * (((xt + 1) / 2) | 1), fp = (xt % 2) ? xt : xt + 1;
-    const size_t smem = 2 * ((size_t)p->N * (MR + bh - 1) * rp * 2 + 16) + 2 * ((size_t)npos * 4 + 16) + (size_t)(p->N + 1) * MR * fp * 8 + 16 * 1024;
+    const size_t smem = 2 * ((size_t)p->N * (mr + bh - 1) * rp * 2 + 16) + 2 * ((size_t)npos * 4 + 16) + (size_t)(p->N + 1) * mr * fp * 8 + 16 * 1024;
     return smem <= 227 * 1024;
 }
 
