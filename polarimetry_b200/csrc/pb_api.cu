@@ -72,7 +72,6 @@ struct pb_ctx {
     int outs_cap = 0, outs_pos = 0;
     double *acc_dev = nullptr;        // stats accumulators
     cudaStream_t hs[2] = {nullptr, nullptr};
-    cudaEvent_t hev[2] = {nullptr, nullptr};
     cudaEvent_t ws_event = nullptr;   // recorded after the last kernel that used the shared workspace
 };
 
@@ -156,7 +155,7 @@ int pb_destroy(pb_ctx *ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
-    for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); if (ctx->hev[k]) cudaEventDestroy(ctx->hev[k]); }
+    for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); }
     if (ctx->ws_event) cudaEventDestroy(ctx->ws_event);
     delete ctx;
     return PB_OK;
@@ -565,7 +564,6 @@ int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, in
     CK(cudaDeviceSynchronize());   // synchronous API: earlier asynchronous work of this context may still use the workspace
     for (int k = 0; k < 2; ++k) {
         if (!ctx->hs[k]) CK(cudaStreamCreateWithFlags(&ctx->hs[k], cudaStreamNonBlocking));
-        if (!ctx->hev[k]) CK(cudaEventCreateWithFlags(&ctx->hev[k], cudaEventDisableTiming));
     }
     const long long P = (long long)p->H * p->W;
     const size_t esz = dtype_size(p->dtype), sbytes = (size_t)p->N * P * esz;

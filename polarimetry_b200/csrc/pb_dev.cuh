@@ -74,8 +74,6 @@ __device__ __forceinline__ double pb_pymod(double a, double b) {
     return pb_pymod_general(a, b);
 }
 
-template <typename T> __device__ __forceinline__ double pb_to_double(T v) { return (double)v; }
-
 // vector loads of PX consecutive elements (callers guarantee alignment when PX > 1)
 template <typename T, int PX> struct VecLoad;
 template <typename T> struct VecLoad<T, 1> {

@@ -362,3 +362,22 @@ def test_drop_in_functions_with_reference_signatures(eng):
     assert np.allclose(ds.chi2[m], g['chi2'][m], rtol=1e-12, atol=0)
     assert np.isnan(ds.field[:, ~mask]).all() and util.eq(ds.field[:, mask], rs.binning(rs.preprocess(v, p), p.bins)[:, mask])
     api._default_engine = None
+
+
+def test_time_series_per_frame_histograms(eng):
+    """Time-series mode (BASELINE configs[4] semantics): per-frame histograms [frames, groups, vars, nbins] from one launch,
+    each equal to the oracle's histogram of that frame; their sum equals the batch histogram."""
+    from polarimetry_b200 import synth
+    frames = np.stack([synth.stack_1pf(40, 72, 18, seed=300 + k) for k in range(4)])
+    cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
+    ocal = util.load_disk(cases.DISK_NODIST)
+    for bins in ((1, 1), (3, 3)):
+        p = AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=38000.0)
+        o = eng.analyze_batch(frames, p, cal, hist_per_stack=True)
+        per = o['hist'].cpu().numpy()
+        assert per.shape == (4, 1, 2, 60)
+        tot = eng.analyze_batch(frames, p, cal)['hist'].cpu().numpy()
+        assert util.eq(per.sum(axis=0), tot[0])
+        for k in range(4):
+            ref = rs.analyze_stack(frames[k], rs.Params(method='1PF', dark=480.0, bins=bins, ilow=38000.0), ocal)
+            assert util.eq(per[k, 0, 0], ref['hist'][('Rho', None)]) and util.eq(per[k, 0, 1], ref['hist'][('Psi', None)])
