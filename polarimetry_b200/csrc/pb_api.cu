@@ -171,6 +171,14 @@ int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, co
     for (size_t k = 0; k < t.size(); ++k) { t[k].x = rho[k]; t[k].y = psi[k]; }
     CK(cudaDeviceSynchronize());
     if (ctx->lut_dev) { cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); ctx->lut_dev = nullptr; ctx->grid_dev = nullptr; ctx->hy_dev = nullptr; }
+    // the cell search corrects an arithmetic guess by at most one cell: the grid must be (numerically) uniform, as the
+    // reference's always is (np.linspace(-1, 1, NbMapValues), PC:463)
+    {
+        const double step = (grid[n - 1] - grid[0]) / (double)(n - 1);
+        for (int k = 0; k < n; ++k)
+            if (!(fabs(grid[k] - (grid[0] + k * step)) <= 0.25 * fabs(step)) || !(step > 0.0))
+                return fail(ctx, PB_ERR_UNSUPPORTED, "pb_set_diskcone: the grid must be uniform (np.linspace), as in Calibration.define_disk");
+    }
     std::vector<double2> hy((size_t)n - 1);
     for (int k = 0; k + 1 < n; ++k) {
         hy[k].x = grid[k + 1] - grid[k];       // the reference's (grid[i+1] - grid[i]), one rounding
@@ -229,6 +237,14 @@ int pb_set_hist(pb_ctx *ctx, int n_vars, int nbins, const double *edges, const i
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     if (ctx->edges_dev) { cudaFree(ctx->edges_dev); ctx->edges_dev = nullptr; }
+    // the bin search corrects an arithmetic guess by at most one bin: edges must be uniform (np.linspace, PC:367)
+    for (int v = 0; v < n_vars; ++v) {
+        const double *e = edges + (size_t)v * (nbins + 1);
+        const double step = (e[nbins] - e[0]) / (double)nbins;
+        for (int k = 0; k <= nbins; ++k)
+            if (!(step > 0.0) || !(fabs(e[k] - (e[0] + k * step)) <= 0.25 * step))
+                return fail(ctx, PB_ERR_UNSUPPORTED, "pb_set_hist: edges must be uniform and increasing (np.linspace), as in Variable.histo");
+    }
     ctx->n_vars = n_vars; ctx->nbins = nbins; ctx->is_rho_bits = 0;
     if (n_vars == 0) return PB_OK;
     CK(cudaMalloc(&ctx->edges_dev, sizeof(double) * n_vars * (nbins + 1)));

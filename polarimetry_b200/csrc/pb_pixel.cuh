@@ -44,8 +44,10 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
     if (!(d >= e[0]) || !(d <= e[nb])) return;
     int k = (int)((d - e[0]) * a.inv_bin_width[var]);
     k = max(0, min(k, nb - 1));
-    if (d < e[k]) { do { --k; } while (k > 0 && d < e[k]); }
-    else { while (k < nb - 1 && d >= e[k + 1]) ++k; }
+    // the arithmetic guess is verified against the real edges; they are uniform (np.linspace, checked by pb_set_hist),
+    // so the guess is off by at most one bin
+    if (d < e[k]) --k;
+    else if (k < nb - 1 && d >= e[k + 1]) ++k;
     unsigned *c = h.cnt + var * nb + k;
     if (a.simple) {
         atomicAdd(c, 1u);
@@ -70,16 +72,14 @@ __device__ __forceinline__ bool roi_pass(const PixArgs &a, uint32_t bits, double
 // disk-cone LUT cell and normalised distance along one axis: g[i] <= x < g[i+1], last cell closed
 // (scipy RegularGridInterpolator rule); t = (x - g[i]) / (g[i+1] - g[i]). Caller guarantees g[0] <= x <= g[n-1].
 // The arithmetic guess floor((x+1)(n-1)/2) is exact up to one cell for a linspace grid; it is then corrected against
-// the real grid values (loops kept for arbitrary monotone grids, they run at most once for linspace).
+// the real grid values.
 __device__ __forceinline__ int lut_axis(const double *__restrict__ g, const double2 *__restrict__ hy, int n, double half_nm1, double x, double &t) {
     int k = __double2int_rd(fma(x, half_nm1, half_nm1));
     k = max(0, min(k, n - 2));
     double ga = __ldg(g + k), gb = __ldg(g + k + 1);
-    if (x < ga) {
-        do { --k; gb = ga; ga = __ldg(g + k); } while (k > 0 && x < ga);
-    } else if (x >= gb && k < n - 2) {
-        do { ++k; ga = gb; gb = __ldg(g + k + 1); } while (k < n - 2 && x >= gb);
-    }
+    // the grid is uniform (np.linspace, PC:463; checked by pb_set_diskcone): the guess is off by at most one cell
+    if (x < ga) { --k; ga = __ldg(g + k); }
+    else if (x >= gb && k < n - 2) { ++k; ga = gb; }
     // t = (x - ga) / (gb - ga), correctly rounded from the tabulated spacing h = gb - ga and y = RN(1/h)
     // (Markstein: q0 = RN(d y), r = d - q0 h exactly, t = RN(q0 + r y); tests/test_shortcuts.py)
     const double2 c = __ldg(hy + k);
