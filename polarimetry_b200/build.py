@@ -16,7 +16,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libpolarb200.so'
-SOURCES = ['pb_api.cu', 'pb_pixel.cu', 'pb_box.cu', 'pb_march.cu', 'pb_reduce.cu']
+SOURCES = ['pb_march_u16_1.cu', 'pb_march_u16_2.cu', 'pb_pixel.cu', 'pb_march_u8_1.cu', 'pb_march_u8_2.cu', 'pb_api.cu', 'pb_box.cu', 'pb_march.cu',
+           'pb_reduce.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

@@ -1,375 +1,12 @@
-// pb_march.cu -- fused single-pass analysis WITH spatial binning: the stack is read once and the maps,
-// mask and histograms come out, with scipy's two-pass running-sum box filter replayed bit for bit.
-//
-// Replaces, in one kernel: Stack.get_intensity (pypolar_classes.py:260-264), analyze_stack's pre-processing
-// (PyPOLAR.py:2953-2957), Polarimetry.binning (PP:2942-2946), compute_fields (PP:2981-3078), the mask logic
-// (PP:2891/2967) and the histograms (PC:340-369).
-//
-// Why a "row march". scipy.ndimage.uniform_filter1d keeps a running sum along each line,
-//     tmp += ext[k+n-1] - ext[k-1];  out[k] = tmp / n,
-// so along W (the second pass, whose inputs RN(S/bh) are no longer integers) every output carries the
-// rounding history of its whole row from column 0: the bits -- hence the LUT cell, hence the histogram bin
-//  -- can only be reproduced by walking each (plane, row) line sequentially. The first pass
-// (along H) sums integers, which is exact in any order, so it is done as a direct window sum.
-//
-// Decomposition (one CTA = 32 rows of one stack, marching over W in steps of XT extended columns):
-//   loader : raw stack -> shared memory, already dark-subtracted and clamped (uint16), plus the per-position
-//            total-intensity partial sums; next step's global loads are in flight during the phases below.
-//   phase A: one thread per (plane, row) line ("chain"): integer window sum over bh rows, q = RN(S/bh),
-//            tmp += q_new - q_old (register ring of BW), f = RN(tmp/bw) -> shared memory (fp64).
-//            Plane N is the total-intensity image the threshold compares against.
-//   phase B: one thread per pixel of the step: sequential harmonic sums over the N planes in the reference's
-//            order (PP:2987-2994), then the shared per-pixel epilogue (pb_pixel.cuh).
-// Divisions by the bin sizes are the two-instruction correctly rounded form fma(x, rhi, x*rlo) (tests/test_shortcuts.py).
-#include <type_traits>
-#include "pb_pixel.cuh"
+// pb_march.cu -- planning and dispatch of the fused row-march kernel (pb_march_impl.cuh). The kernel is instantiated in
+// four translation units (pb_march_u16_1.cu, ... one per stack type x number of harmonics) so that they compile in parallel.
+#include "pb_march_impl.cuh"
 
-void pb_ddrecip(int n, double *hi, double *lo);   // pb_api.cu
+cudaError_t pb_march_u16_nh1(const PixArgs &a, const Basis1 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
+cudaError_t pb_march_u16_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
+cudaError_t pb_march_u8_nh1(const PixArgs &a, const Basis1 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
+cudaError_t pb_march_u8_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
 
-namespace {
-
-// MR = rows per CTA is a template parameter: 32 (N + 1 <= 32 lines per row), 16 (<= 64) or 8 (<= 128); a chain warp holds
-// 32/MR groups of MR rows
-constexpr int PL = 2;      // planes (lines) per chain thread
-constexpr int QMAX = 2;    // tile positions per loader thread
-constexpr int LA = 6;      // angle planes per loader batch
-
-struct MarchArgs {
-    int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
-    int steps;                   // number of XT-wide steps over the extended row (W + bw - 1)
-    int tile_rows;               // MR + bh - 1
-    int cw, lw;                  // compute (chain + pixel) warps, loader warps
-    int isub, idark;             // dark + removed_intensity, dark (integers on this path)
-    double bh_hi, bh_lo, bw_hi, bw_lo;   // double-double reciprocals of the bin sizes
-    unsigned off_raw, off_T, off_f;      // byte offsets in dynamic shared memory (after the histogram area)
-    unsigned raw_bytes, T_bytes;         // size of ONE buffer of the double-buffered raw / T tiles
-};
-
-template <int BW> struct StepWidth { static constexpr int M = (8 + BW - 1) / BW; static constexpr int XT = BW * M; };
-template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr int XT = 8; };
-
-// SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
-template <typename UT, int NH, int BW, bool SQ, int MR>
-__global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
-    constexpr int SUBS = 32 / MR;                       // line groups per chain warp
-    constexpr int XT = StepWidth<BW>::XT;
-    constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
-    constexpr int RW = ((XT + 1) / 2) | 1;              // raw tile row pitch in 32-bit words (odd: conflict-free chain loads)
-    constexpr int RP = 2 * RW;                          // ... in uint16
-    extern __shared__ __align__(16) unsigned char smem[];
-    const pb_outputs out = a.outs[blockIdx.y];
-    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
-    HistSmem hs;
-    hs.cnt = nullptr; hs.edges = nullptr;
-    if (do_hist) hs = hist_setup(a, smem);
-
-    const int N = a.N, H = a.H, W = a.W;
-    const int y0 = blockIdx.x * MR;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bh = SQ ? BW : ma.bh;
-    const int TR = SQ ? MR + BW - 1 : ma.tile_rows;
-    const int NPOS = TR * XT;
-    const int plane_pitch = TR * RP;                     // uint16 per plane of the raw tile
-    const int steps = ma.steps;
-
-    if (warp >= ma.cw) {
-        // =========================== loader warps ===========================
-        // raw stack -> shared memory, dark-subtracted and clamped (PP:2953), for step t+1 while the compute warps work on step t;
-        // also the per-position total-intensity sums sum_i max(v - dark, 0) (PC:261) for the threshold image.
-        const UT *stack = reinterpret_cast<const UT *>(a.stack) + (long long)blockIdx.y * a.stack_stride;
-        asm volatile("" : "+l"(stack));
-        const int ltid = tid - ma.cw * 32, LT = ma.lw * 32;
-        const int isub = ma.isub, idark = ma.idark;
-        const bool sep = isub != idark;
-        const unsigned uP = (unsigned)a.P;
-        unsigned rowoff[QMAX];
-        int jj[QMAX], soff[QMAX];
-#pragma unroll
-        for (int q = 0; q < QMAX; ++q) {
-            const int pos = ltid + q * LT;
-            const int r = pos / XT;
-            jj[q] = pos - r * XT;
-            soff[q] = r * RP + jj[q];
-            rowoff[q] = pos < NPOS ? (unsigned)pb_reflect(y0 - ma.hh + r, H) * (unsigned)W : 0u;
-            if (pos >= NPOS) jj[q] = -1;
-        }
-        for (int t = 0; t <= steps; ++t) {
-            // fill buffer t&1 with the data of step t (t == steps: nothing left, just take part in the barriers)
-            if (t < steps) {
-                uint16_t *rawb = reinterpret_cast<uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
-                int *Tb = reinterpret_cast<int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
-                unsigned off[QMAX];
-                int tsum[QMAX];
-#pragma unroll
-                for (int q = 0; q < QMAX; ++q) {
-                    off[q] = rowoff[q] + (unsigned)(jj[q] >= 0 ? pb_reflect(t * XT + jj[q] - ma.hw, W) : 0);
-                    tsum[q] = 0;
-                }
-                // running plane pointers kept opaque so that the 64-bit stack base is not re-derived for every load:
-                // per element one address IMAD.WIDE, the load, the fused subtract/clamp, the store and half an add
-                const UT *bp = stack;
-                uint16_t *dst = rawb;
-                int i = 0;
-                for (; i + LA <= N; i += LA) {            // LA planes x QMAX positions of loads in flight before any is consumed
-                    asm volatile("" : "+l"(bp));
-                    unsigned v[LA][QMAX];
-                    const UT *b = bp;
-#pragma unroll
-                    for (int l = 0; l < LA; ++l) {
-#pragma unroll
-                        for (int q = 0; q < QMAX; ++q) v[l][q] = (unsigned)__ldg(b + off[q]);
-                        b += uP;
-                    }
-#pragma unroll
-                    for (int q = 0; q < QMAX; ++q) {
-                        if (jj[q] >= 0) {
-#pragma unroll
-                            for (int l = 0; l < LA; ++l) {
-                                const int f = max((int)v[l][q] - isub, 0);
-                                dst[soff[q] + l * plane_pitch] = (uint16_t)f;
-                                tsum[q] += sep ? max((int)v[l][q] - idark, 0) : f;
-                            }
-                        }
-                    }
-                    bp += (size_t)LA * uP;
-                    dst += LA * plane_pitch;
-                }
-                for (; i < N; ++i) {
-                    asm volatile("" : "+l"(bp));
-#pragma unroll
-                    for (int q = 0; q < QMAX; ++q) {
-                        if (jj[q] >= 0) {
-                            const int v = (int)__ldg(bp + off[q]);
-                            const int f = max(v - isub, 0);
-                            dst[soff[q]] = (uint16_t)f;
-                            tsum[q] += sep ? max(v - idark, 0) : f;
-                        }
-                    }
-                    bp += uP;
-                    dst += plane_pitch;
-                }
-#pragma unroll
-                for (int q = 0; q < QMAX; ++q)
-                    if (jj[q] >= 0) Tb[ltid + q * LT] = tsum[q];
-            }
-            __syncthreads();                 // end-of-step barrier: buffer t&1 complete, step t-1 fully consumed
-        }
-    } else {
-        // =========================== compute warps ===========================
-        double *fbuf = reinterpret_cast<double *>(smem + ma.off_f);           // [N+1][MR][FP]
-        const int crow = lane % MR;                                            // chains (plane0 .. plane0+PL-1, row y0 + crow)
-        const int plane0 = (warp * SUBS + lane / MR) * PL;
-        // chain state: running sum and the last BW first-pass outputs. The ring starts at 0.0 so that the first BW steps
-        // compute tmp + (q - 0.0) = tmp + q, i.e. scipy's left-to-right initial window sum, with the same instruction.
-        double tmp[PL], ring[PL][BW];
-#pragma unroll
-        for (int c = 0; c < PL; ++c) {
-            tmp[c] = 0.0;
-#pragma unroll
-            for (int s = 0; s < BW; ++s) ring[c][s] = 0.0;
-        }
-        double *const cfo = fbuf + (plane0 * MR + crow) * FP;
-        const int pr = tid / XT, pj = tid - pr * XT;                           // pixel role
-        const bool pix = tid < MR * XT && (y0 + pr) < H;
-        const double *const pfp = fbuf + pr * FP + pj;
-        const bool f64 = a.flags & PB_FLAG_OUT_F64;
-        __syncthreads();                      // tile of step 0 in place
-        for (int t = 0; t < steps; ++t) {
-            const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
-            const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
-            // ---- phase A: the (plane, row) lines advance XT extended positions
-            // one step of a line: q = RN(S1 / bh) [(double)S1 = (2^52 + S1) - 2^52 exactly; H pass skipped if bh <= 1, PP:2944],
-            // tmp += q - ring (W pass, skipped if BW == 1), f = RN(tmp / bw)
-            auto line_step = [&](int c, int j, int S1) -> double {
-                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-                const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-                if constexpr (BW == 1) {
-                    return q;
-                } else {
-                    const double old = ring[c][j % BW];
-                    ring[c][j % BW] = q;
-                    tmp[c] = tmp[c] + (q - old);
-                    return fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
-                }
-            };
-            if (plane0 + PL <= N) {
-                // all PL lines of this thread are image planes: interleave them position by position so that their
-                // (independent) running-sum dependency chains overlap
-                const uint16_t *rp = rawb + plane0 * plane_pitch + crow * RP;
-#pragma unroll
-                for (int j = 0; j < XT; ++j) {
-#pragma unroll
-                    for (int c = 0; c < PL; ++c) {
-                        int S1 = 0;
-                        if constexpr (SQ) {
-#pragma unroll
-                            for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
-                        } else {
-                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
-                        }
-                        cfo[c * (MR * FP) + j] = line_step(c, j, S1);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < PL; ++c) {
-                    const int plane = plane0 + c;
-                    double *fo = cfo + c * (MR * FP);
-                    if (plane < N) {
-                        const uint16_t *rp = rawb + plane * plane_pitch + crow * RP;
-#pragma unroll
-                        for (int j = 0; j < XT; ++j) {
-                            int S1 = 0;
-                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP + j];
-                            fo[j] = line_step(c, j, S1);
-                        }
-                    } else if (plane == N) {
-                        // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
-                        const int *tp = Tb + crow * XT;
-#pragma unroll
-                        for (int j = 0; j < XT; ++j) {
-                            int S1 = 0;
-                            for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT + j];
-                            fo[j] = line_step(c, j, S1);
-                        }
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"r"(ma.cw * 32) : "memory");   // compute warps only: fbuf of step t complete
-            // ---- phase B: the pixels completed by this step
-            const int k = t * XT + pj - (BW - 1);
-            if (pix && k >= 0 && k < W) {
-                const long long p = (long long)(y0 + pr) * W + k;
-                const double I = pfp[N * (MR * FP)];             // plane N: the binned total intensity
-                // the threshold / ROI test needs only I: pixels that fail it skip the harmonic sums altogether
-                // (their maps are NaN whatever the sums are, PP:3017-3025 / PP:3052)
-                bool cand;
-                if (a.simple) cand = I >= a.roi_ilow[0];
-                else if (a.mask_in) cand = __ldg(a.mask_in + p) != 0;
-                else cand = roi_pass(a, a.roi_bits ? __ldg(a.roi_bits + p) : 1u, I);
-                PixOut o;
-                o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
-                o.m = false;
-                if (cand) {
-                    double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
-                    const double *fp = pfp;
-#pragma unroll 6
-                    for (int i = 0; i < N; ++i) {
-                        const double f = *fp;
-                        fp += MR * FP;
-                        S0 = S0 + f;
-                        Sc = Sc + f * bs.c2[i];
-                        Ss = Ss + f * bs.s2[i];
-                        if constexpr (NH == 2) {
-                            Sc4 = Sc4 + f * bs.c4[i];
-                            Ss4 = Ss4 + f * bs.s4[i];
-                        }
-                        Sff = fma(f, f, Sff);                    // screening only
-                    }
-                    HarmPix hp = harm_stage_a<NH>(a, p, S0, Sc, Ss, Sc4, Ss4, Sff, I);
-                    if (hp.need) {
-                        ExactAcc ex;
-                        ex.init();
-                        for (int i = 0; i < N; ++i) {
-                            double c4 = 0.0, s4 = 0.0;
-                            if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-                            ex.template step<NH>(hp, pfp[i * (MR * FP)], bs.c2[i], bs.s2[i], c4, s4);
-                        }
-                        hp.m = ex.decide(a);
-                    }
-                    o = harm_stage_b<NH>(a, hs, do_hist, hp);
-                }
-                store_pixel<NH>(a, out, p, o, I, f64);
-            }
-            __syncthreads();                  // end-of-step barrier (all warps): fbuf free again, tile of step t+1 in place
-        }
-    }
-    if (do_hist) hist_flush(a, hs, out.hist);
-}
-
-size_t hist_bytes(const PixArgs &a) {
-    size_t b = sizeof(double) * a.n_vars * (a.nbins + 1) + sizeof(unsigned) * a.n_groups * a.n_vars * a.nbins;
-    return (b + 15) & ~(size_t)15;
-}
-
-template <typename UT, int NH, int BW, int MR>
-cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
-    constexpr int XT = StepWidth<BW>::XT;
-    constexpr int FP = (XT % 2) ? XT : XT + 1;
-    constexpr int RP = 2 * (((XT + 1) / 2) | 1);
-    constexpr int SUBS = 32 / MR;
-    MarchArgs ma;
-    const int bh = p->bin_h > 1 ? p->bin_h : 1;
-    ma.bh = bh; ma.hh = bh / 2; ma.hw = BW / 2;
-    ma.steps = (a.W + BW - 1 + XT - 1) / XT;
-    ma.tile_rows = MR + bh - 1;
-    ma.isub = (int)a.sub; ma.idark = (int)a.dark;
-    const int npos = ma.tile_rows * XT;
-    const int groups = (a.N + 1 + PL - 1) / PL;             // PL lines per chain thread
-    ma.cw = (groups + SUBS - 1) / SUBS;
-    if (ma.cw * 32 < MR * XT) ma.cw = (MR * XT + 31) / 32;
-    ma.lw = (npos + 32 * QMAX - 1) / (32 * QMAX);
-    if (ma.lw < 2 && npos > 32 * 3) ma.lw = 2;
-    const int threads = 32 * (ma.cw + ma.lw);
-    if (threads > 1024 || a.P >= 2147483647LL) return cudaErrorInvalidConfiguration;
-    pb_ddrecip(bh, &ma.bh_hi, &ma.bh_lo);
-    pb_ddrecip(BW, &ma.bw_hi, &ma.bw_lo);
-    size_t off = hist_bytes(a);
-    ma.raw_bytes = (unsigned)(((size_t)a.N * ma.tile_rows * RP * 2 + 15) & ~(size_t)15);
-    ma.T_bytes = (unsigned)(((size_t)npos * 4 + 15) & ~(size_t)15);
-    ma.off_raw = (unsigned)off; off += 2 * (size_t)ma.raw_bytes;
-    ma.off_T = (unsigned)off; off += 2 * (size_t)ma.T_bytes;
-    ma.off_f = (unsigned)off; off += (size_t)(a.N + 1) * MR * FP * 8;
-    if (off > 227 * 1024) return cudaErrorInvalidConfiguration;
-    dim3 grid((a.H + MR - 1) / MR, n_stacks);
-    cudaError_t e;
-    if (bh == BW && BW > 1) {
-        auto kern = k_march<UT, NH, BW, true, MR>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
-        kern<<<grid, threads, off, st>>>(a, bs, ma);
-    } else {
-        if constexpr (MR == 32) {
-            auto kern = k_march<UT, NH, BW, false, MR>;
-            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off)) != cudaSuccess) return e;
-            kern<<<grid, threads, off, st>>>(a, bs, ma);
-        } else {
-            return cudaErrorInvalidConfiguration;       // rectangular windows with more than 31 angles: unfused kernels
-        }
-    }
-    return cudaGetLastError();
-}
-
-template <typename UT, int NH, int MR>
-cudaError_t launch_mr(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
-    const int bw = p->bin_w > 1 ? p->bin_w : 1;
-    switch (bw) {
-    case 1: if constexpr (MR == 32) return launch_bw<UT, NH, 1, MR>(a, bs, p, n_stacks, st); else return cudaErrorInvalidConfiguration;
-    case 2: return launch_bw<UT, NH, 2, MR>(a, bs, p, n_stacks, st);
-    case 3: return launch_bw<UT, NH, 3, MR>(a, bs, p, n_stacks, st);
-    case 4: return launch_bw<UT, NH, 4, MR>(a, bs, p, n_stacks, st);
-    case 5: return launch_bw<UT, NH, 5, MR>(a, bs, p, n_stacks, st);
-    case 6: return launch_bw<UT, NH, 6, MR>(a, bs, p, n_stacks, st);
-    case 7: return launch_bw<UT, NH, 7, MR>(a, bs, p, n_stacks, st);
-    case 8: return launch_bw<UT, NH, 8, MR>(a, bs, p, n_stacks, st);
-    }
-    return cudaErrorInvalidConfiguration;
-}
-
-// rows per CTA from the number of lines per row (N planes + the intensity plane)
-int march_rows(int N) { return N + 1 <= 32 ? 32 : (N + 1 <= 64 ? 16 : 8); }
-
-template <typename UT, int NH>
-cudaError_t launch_nh(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
-    const int mr = march_rows(a.N);
-    if (mr == 32) return launch_mr<UT, NH, 32>(a, bs, p, n_stacks, st);
-    if constexpr (std::is_same<UT, uint16_t>::value) {      // the many-angle variants are built for uint16 stacks only
-        if (mr == 16) return launch_mr<UT, NH, 16>(a, bs, p, n_stacks, st);
-        return launch_mr<UT, NH, 8>(a, bs, p, n_stacks, st);
-    }
-    return cudaErrorInvalidConfiguration;
-}
-
-}  // namespace
 
 // The march kernel covers: harmonic modalities without sqrt (1PF, SRS, SHG, 2PF), integer stacks, integer-valued
 // dark / dark+removed (so that the H pass sums integers), bin_w <= 8, N + 1 <= 32 chain warps. Everything else
@@ -404,9 +41,9 @@ cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params 
         Basis1 b1;
         memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));
         memcpy(b1.kc2, bs.kc2, sizeof(b1.kc2)); memcpy(b1.ks2, bs.ks2, sizeof(b1.ks2));
-        e = p->dtype == PB_U8 ? launch_nh<uint8_t, 1>(a, b1, p, n_stacks, st) : launch_nh<uint16_t, 1>(a, b1, p, n_stacks, st);
+        e = p->dtype == PB_U8 ? pb_march_u8_nh1(a, b1, p, n_stacks, st) : pb_march_u16_nh1(a, b1, p, n_stacks, st);
     } else {
-        e = p->dtype == PB_U8 ? launch_nh<uint8_t, 2>(a, bs, p, n_stacks, st) : launch_nh<uint16_t, 2>(a, bs, p, n_stacks, st);
+        e = p->dtype == PB_U8 ? pb_march_u8_nh2(a, bs, p, n_stacks, st) : pb_march_u16_nh2(a, bs, p, n_stacks, st);
     }
     if (e == cudaSuccess && launches) ++*launches;
     return e;
