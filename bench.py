@@ -164,7 +164,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--bin', type=int, default=int(os.environ.get('PB_BENCH_BIN', '3')))
     ap.add_argument('--batch', type=int, default=int(os.environ.get('PB_BENCH_BATCH', '16')), help='stacks resident per GPU')
-    ap.add_argument('--e2e-batch', type=int, default=4)
+    ap.add_argument('--e2e-batch', type=int, default=8)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--ilow', type=float, default=ILOW, help='intensity threshold (1pf workload); 0 keeps every pixel')
@@ -289,8 +289,21 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = Be * H * W * N * world * e2e_steps / float(te.item()) / 1e6
+    # PCIe ceiling of this box for the same buffers: pinned H2D of the input batch alone (what bounds e2e)
+    dprobe = torch.empty_like(host, device=dev)
+    evp = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    dprobe.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    evp[0].record()
+    for _ in range(3):
+        dprobe.copy_(host, non_blocking=True)
+    evp[1].record()
+    torch.cuda.synchronize()
+    h2d_gbs = 3 * host.numel() * 2 / (evp[0].elapsed_time(evp[1]) * 1e-3) / 1e9
+    del dprobe
     e2e = {'value': e2e_val, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': Be * H * W * N * 2,
-           'd2h_bytes_per_step': Be * (H * W * out_bpp) + 2 * 60 * 8, 'stacks_per_step': Be,
+           'd2h_bytes_per_step': Be * (H * W * out_bpp) + 2 * 60 * 8, 'stacks_per_step': Be, 'h2d_pinned_gbs': round(h2d_gbs, 2),
+           'frac_of_h2d_ceiling': round(e2e_val * 1e6 * 2 / 1e9 / h2d_gbs, 3),
            'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
 
     cpu = None

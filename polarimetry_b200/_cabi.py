@@ -8,7 +8,8 @@ import ctypes as C
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / 'libpolarb200.so'
+import os
+LIB_PATH = Path(os.environ['PB_LIB']) if os.environ.get('PB_LIB') else PKG / 'libpolarb200.so'   # PB_LIB: developer A/B builds
 
 PB_MAX_ROIS, PB_MAX_VARS, PB_MAX_BINS = 32, 4, 128
 FLAG_OUT_F64, FLAG_NO_HIST, FLAG_EXACT_CHI2, FLAG_FORCE_UNFUSED = 1, 2, 4, 8

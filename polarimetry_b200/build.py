@@ -15,7 +15,8 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
-LIB = PKG / 'libpolarb200.so'
+TAG = os.environ.get('PB_BUILD_TAG', '')          # developer A/B builds: libpolarb200_<tag>.so (select with PB_LIB=...)
+LIB = PKG / (f'libpolarb200_{TAG}.so' if TAG else 'libpolarb200.so')
 SOURCES = ['pb_march_u16_1.cu', 'pb_march_u16_2.cu', 'pb_pixel.cu', 'pb_march_u8_1.cu', 'pb_march_u8_2.cu', 'pb_api.cu', 'pb_box.cu', 'pb_march.cu',
            'pb_reduce.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
@@ -34,10 +35,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not _stale():
         return LIB
     objs = []
-    (PKG / 'build').mkdir(exist_ok=True)
+    bdir = PKG / 'build' / TAG if TAG else PKG / 'build'
+    bdir.mkdir(parents=True, exist_ok=True)
     procs = []
     for s in SOURCES:
-        o = PKG / 'build' / (s + '.o')
+        o = bdir / (s + '.o')
         cmd = ['nvcc', *NVCC_FLAGS, *os.environ.get('PB_EXTRA_NVCC', '').split(), '-c', str(CSRC / s), '-o', str(o)] + (['-Xptxas', '-v'] if verbose else [])
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(o))

@@ -72,6 +72,8 @@ struct pb_ctx {
     int outs_cap = 0, outs_pos = 0;
     double *acc_dev = nullptr;        // stats accumulators
     cudaStream_t hs[2] = {nullptr, nullptr};
+    int64_t *hist_pinned = nullptr;   // pinned staging of the per-stack histograms of pb_analyze_host
+    size_t hist_pinned_n = 0;
     cudaEvent_t ws_event = nullptr;   // recorded after the last kernel that used the shared workspace
 };
 
@@ -156,6 +158,7 @@ int pb_destroy(pb_ctx *ctx) {
     cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); }
+    if (ctx->hist_pinned) cudaFreeHost(ctx->hist_pinned);
     if (ctx->ws_event) cudaEventDestroy(ctx->ws_event);
     delete ctx;
     return PB_OK;
@@ -598,7 +601,16 @@ int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, in
     if (edge_host) { edge_dev = (double *)extra; CK(cudaMemcpyAsync(edge_dev, edge_host, P * 8, cudaMemcpyHostToDevice, ctx->hs[0])); }
     if (roi_bits_host) { roi_dev = (uint32_t *)(extra + P * 8); CK(cudaMemcpyAsync(roi_dev, roi_bits_host, P * 4, cudaMemcpyHostToDevice, ctx->hs[0])); }
     CK(cudaStreamSynchronize(ctx->hs[0]));
-    std::vector<int64_t> htmp((size_t)n_stacks * nhist);
+    // per-stack histograms come back through PINNED staging: a device-to-host copy into pageable memory would block the
+    // host until the stream drains and serialise the whole copy/compute pipeline
+    const size_t nh_all = (size_t)n_stacks * nhist;
+    if (nh_all > ctx->hist_pinned_n) {
+        if (ctx->hist_pinned) cudaFreeHost(ctx->hist_pinned);
+        ctx->hist_pinned = nullptr; ctx->hist_pinned_n = 0;
+        CK(cudaHostAlloc((void **)&ctx->hist_pinned, sizeof(int64_t) * nh_all, cudaHostAllocDefault));
+        ctx->hist_pinned_n = nh_all;
+    }
+    int64_t *htmp = ctx->hist_pinned;
     // the unfused path shares the context workspace between stacks: keep it on one stream
     const bool serial = std::string(plan_name(ctx, p)) == "unfused";
     for (int s = 0; s < n_stacks; ++s) {
@@ -627,7 +639,7 @@ int pb_analyze_host(pb_ctx *ctx, const pb_params *p, const void *stacks_host, in
         if (oh.rho_contour) CK(cudaMemcpyAsync(oh.rho_contour, od.rho_contour, P * msz, cudaMemcpyDeviceToHost, st));
         if (oh.intensity) CK(cudaMemcpyAsync(oh.intensity, od.intensity, P * 8, cudaMemcpyDeviceToHost, st));
         if (oh.mask) CK(cudaMemcpyAsync(oh.mask, od.mask, P, cudaMemcpyDeviceToHost, st));
-        if (oh.hist) CK(cudaMemcpyAsync(htmp.data() + (size_t)s * nhist, od.hist, sizeof(int64_t) * nhist, cudaMemcpyDeviceToHost, st));
+        if (oh.hist) CK(cudaMemcpyAsync(htmp + (size_t)s * nhist, od.hist, sizeof(int64_t) * nhist, cudaMemcpyDeviceToHost, st));
         // slot k is reused by stack s+2: that stack's H2D is enqueued on the same stream, hence ordered after these copies
     }
     CK(cudaStreamSynchronize(ctx->hs[0]));

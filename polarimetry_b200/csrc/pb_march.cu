@@ -22,7 +22,7 @@ bool pb_march_supported(const pb_params *p) {
     const int bh = p->bin_h > 1 ? p->bin_h : 1, bw = p->bin_w > 1 ? p->bin_w : 1;
     const int mr = march_rows(p->N);
     if (mr != 32 && (p->dtype != PB_U16 || bh != bw || bw < 2)) return false;   // many angles: uint16, square windows
-    const int xt = bw == 1 ? 8 : bw * ((8 + bw - 1) / bw);
+    const int xt = bw == 1 ? 8 : bw * ((PB_MARCH_XT_MIN + bw - 1) / bw);
     const int subs = 32 / mr;
     int cw = (((p->N + 1 + PL - 1) / PL) + subs - 1) / subs;
     if (cw * 32 < mr * xt) cw = (mr * xt + 31) / 32;

@@ -22,6 +22,7 @@
 //            order (PP:2987-2994), then the shared per-pixel epilogue (pb_pixel.cuh).
 // Divisions by the bin sizes are the two-instruction correctly rounded form fma(x, rhi, x*rlo) (tests/test_shortcuts.py).
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 #include "pb_pixel.cuh"
 
@@ -46,7 +47,10 @@ struct MarchArgs {
     unsigned raw_bytes, T_bytes;         // size of ONE buffer of the double-buffered raw / T tiles
 };
 
-template <int BW> struct StepWidth { static constexpr int M = (8 + BW - 1) / BW; static constexpr int XT = BW * M; };
+#ifndef PB_MARCH_XT_MIN
+#define PB_MARCH_XT_MIN 8          // step width: the smallest multiple of the W window >= this
+#endif
+template <int BW> struct StepWidth { static constexpr int M = (PB_MARCH_XT_MIN + BW - 1) / BW; static constexpr int XT = BW * M; };
 template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr int XT = 8; };
 
 // SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
@@ -157,7 +161,6 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
         }
     } else {
         // =========================== compute warps ===========================
-        double *fbuf = reinterpret_cast<double *>(smem + ma.off_f);           // [N+1][MR][FP]
         const int crow = lane % MR;                                            // chains (plane0 .. plane0+PL-1, row y0 + crow)
         const int plane0 = (warp * SUBS + lane / MR) * PL;
         // chain state: running sum and the last BW first-pass outputs. The ring starts at 0.0 so that the first BW steps
@@ -169,46 +172,78 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
 #pragma unroll
             for (int s = 0; s < BW; ++s) ring[c][s] = 0.0;
         }
-        double *const cfo = fbuf + (plane0 * MR + crow) * FP;
+        const int cfo_off = (plane0 * MR + crow) * FP;
         const int pr = tid / XT, pj = tid - pr * XT;                           // pixel role
         const bool pix = tid < MR * XT && (y0 + pr) < H;
-        const double *const pfp = fbuf + pr * FP + pj;
+        const int pfp_off = pr * FP + pj;
         const bool f64 = a.flags & PB_FLAG_OUT_F64;
-        __syncthreads();                      // tile of step 0 in place
-        for (int t = 0; t < steps; ++t) {
+        const bool lean = store_is_lean<NH>(a, out);
+
+        // ---- phase A: the (plane, row) lines advance XT extended positions: tile of step t -> filtered tile
+        // one step of a line: q = RN(S1 / bh) [(double)S1 = (2^52 + S1) - 2^52 exactly; H pass skipped if bh <= 1, PP:2944],
+        // tmp += q - ring (W pass, skipped if BW == 1), f = RN(tmp / bw)
+        auto line_step = [&](int c, int j, int S1) -> double {
+            const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+            const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+            if constexpr (BW == 1) {
+                return q;
+            } else {
+                const double old = ring[c][j % BW];
+                ring[c][j % BW] = q;
+                tmp[c] = tmp[c] + (q - old);
+                return fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+            }
+        };
+        auto phase_a = [&](int t) {
             const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
             const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
-            // ---- phase A: the (plane, row) lines advance XT extended positions
-            // one step of a line: q = RN(S1 / bh) [(double)S1 = (2^52 + S1) - 2^52 exactly; H pass skipped if bh <= 1, PP:2944],
-            // tmp += q - ring (W pass, skipped if BW == 1), f = RN(tmp / bw)
-            auto line_step = [&](int c, int j, int S1) -> double {
-                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-                const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-                if constexpr (BW == 1) {
-                    return q;
-                } else {
-                    const double old = ring[c][j % BW];
-                    ring[c][j % BW] = q;
-                    tmp[c] = tmp[c] + (q - old);
-                    return fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
-                }
-            };
+            double *const cfo = reinterpret_cast<double *>(smem + ma.off_f) + cfo_off;
             if (plane0 + PL <= N) {
-                // all PL lines of this thread are image planes: interleave them position by position so that their
-                // (independent) running-sum dependency chains overlap
-                const uint16_t *rp = rawb + plane0 * plane_pitch + crow * RP;
+                // all PL lines of this thread are image planes. Blocks of JB positions, each in three stages -- all the
+                // shared-memory loads and the independent first-pass quotients, then the (only) sequential part, the two
+                // running sums, then the stores -- so that the independent fp64 chains overlap instead of running one
+                // after the other (the compiler cannot move the tile loads across the filtered-tile stores by itself)
+                constexpr int JB = (BW == 1) ? 4 : BW;
+                const uint16_t *__restrict__ rp = rawb + plane0 * plane_pitch + crow * RP;
 #pragma unroll
-                for (int j = 0; j < XT; ++j) {
+                for (int j0 = 0; j0 < XT; j0 += JB) {
+                    double q[JB][PL];
 #pragma unroll
-                    for (int c = 0; c < PL; ++c) {
-                        int S1 = 0;
-                        if constexpr (SQ) {
+                    for (int jj = 0; jj < JB; ++jj) {
 #pragma unroll
-                            for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
-                        } else {
-                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j];
+                        for (int c = 0; c < PL; ++c) {
+                            if (j0 + jj < XT) {
+                                int S1 = 0;
+                                if constexpr (SQ) {
+#pragma unroll
+                                    for (int dy = 0; dy < BW; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j0 + jj];
+                                } else {
+                                    for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[c * plane_pitch + dy * RP + j0 + jj];
+                                }
+                                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+                                q[jj][c] = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+                            }
                         }
-                        cfo[c * (MR * FP) + j] = line_step(c, j, S1);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < JB; ++jj) {
+#pragma unroll
+                        for (int c = 0; c < PL; ++c) {
+                            if (j0 + jj < XT) {
+                                if constexpr (BW > 1) {
+                                    const double d = q[jj][c] - ring[c][(j0 + jj) % BW];
+                                    ring[c][(j0 + jj) % BW] = q[jj][c];
+                                    tmp[c] = tmp[c] + d;
+                                    q[jj][c] = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < JB; ++jj) {
+#pragma unroll
+                        for (int c = 0; c < PL; ++c)
+                            if (j0 + jj < XT) cfo[c * (MR * FP) + j0 + jj] = q[jj][c];
                     }
                 }
             } else {
@@ -236,8 +271,10 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                     }
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"r"(ma.cw * 32) : "memory");   // compute warps only: fbuf of step t complete
-            // ---- phase B: the pixels completed by this step
+        };
+        // ---- phase B: the pixels completed by step t
+        auto phase_b = [&](int t) {
+            const double *const pfp = reinterpret_cast<const double *>(smem + ma.off_f) + pfp_off;
             const int k = t * XT + pj - (BW - 1);
             if (pix && k >= 0 && k < W) {
                 const long long p = (long long)(y0 + pr) * W + k;
@@ -251,6 +288,10 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                 PixOut o;
                 o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
                 o.m = false;
+                if (!cand && lean) {
+                    store_invalid_lean<NH>(a, out, p);
+                    return;
+                }
                 if (cand) {
                     double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
                     const double *fp = pfp;
@@ -280,9 +321,16 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                     }
                     o = harm_stage_b<NH>(a, hs, do_hist, hp);
                 }
-                store_pixel<NH>(a, out, p, o, I, f64);
+                store_pixel<NH>(a, out, p, o, I, f64, lean);
             }
-            __syncthreads();                  // end-of-step barrier (all warps): fbuf free again, tile of step t+1 in place
+        };
+
+        __syncthreads();                      // tile of step 0 in place
+        for (int t = 0; t < steps; ++t) {
+            phase_a(t);
+            asm volatile("bar.sync 1, %0;" ::"r"(ma.cw * 32) : "memory");   // compute warps only: filtered tile of step t complete
+            phase_b(t);
+            __syncthreads();                  // end-of-step barrier (all warps): filtered tile free again, tile of step t+1 in place
         }
     }
     if (do_hist) hist_flush(a, hs, out.hist);
@@ -356,14 +404,28 @@ cudaError_t launch_mr(const PixArgs &a, const typename BasisSel<NH>::type &bs, c
     return cudaErrorInvalidConfiguration;
 }
 
-// rows per CTA from the number of lines per row (N planes + the intensity plane)
-int march_rows(int N) { return N + 1 <= 32 ? 32 : (N + 1 <= 64 ? 16 : 8); }
+// rows per CTA from the number of lines per row (N planes + the intensity plane); PB_MARCH_ROWS=8|16|32 is a tuning knob
+int march_rows_forced() {
+    static const int forced = [] { const char *e = getenv("PB_MARCH_ROWS"); return e ? atoi(e) : 0; }();
+    return forced;
+}
+int march_rows(int N) {
+    const int need = N + 1 <= 32 ? 32 : (N + 1 <= 64 ? 16 : 8);
+    const int forced = march_rows_forced();
+    return (forced == 16 || forced == 8) && forced < need ? forced : need;
+}
 
 template <typename UT, int NH>
 cudaError_t launch_nh(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
-    const int mr = march_rows(a.N);
+    int mr = march_rows(a.N);
+    if constexpr (std::is_same<UT, uint16_t>::value) {
+        // few stacks (the single-stack drop-in call, the host-buffer pipeline): 32-row CTAs would leave most SMs idle
+        // (2048 rows = 64 CTAs for 148 SMs), so fall to 16 or 8 rows per CTA until the grid covers the machine twice
+        const bool small_ok = p->bin_h == p->bin_w && p->bin_w >= 2 && march_rows_forced() == 0;
+        while (small_ok && mr > 8 && (long long)n_stacks * ((a.H + mr - 1) / mr) < 2 * 148) mr /= 2;
+    }
     if (mr == 32) return launch_mr<UT, NH, 32>(a, bs, p, n_stacks, st);
-    if constexpr (std::is_same<UT, uint16_t>::value) {      // the many-angle variants are built for uint16 stacks only
+    if constexpr (std::is_same<UT, uint16_t>::value) {      // the 16- and 8-row variants are built for uint16 stacks only
         if (mr == 16) return launch_mr<UT, NH, 16>(a, bs, p, n_stacks, st);
         return launch_mr<UT, NH, 8>(a, bs, p, n_stacks, st);
     }

@@ -246,8 +246,29 @@ __device__ __forceinline__ void store1(void *base, long long p, double v, bool f
     if (f64) reinterpret_cast<double *>(base)[p] = v; else reinterpret_cast<float *>(base)[p] = (float)v;
 }
 
+// the common output set of the throughput mode -- float32 maps for every variable + intmap + mask, nothing else -- is
+// recognised once per kernel (uniform) so that the per-pixel store sequence has no per-map pointer / type tests
 template <int NH>
-__device__ __forceinline__ void store_pixel(const PixArgs &a, const pb_outputs &out, long long p, const PixOut &o, double I, bool f64) {
+__device__ __forceinline__ bool store_is_lean(const PixArgs &a, const pb_outputs &out) {
+    bool ok = !(a.flags & PB_FLAG_OUT_F64) && out.var[0] && out.var[1] && out.intmap && out.mask && !out.intensity &&
+              !out.rho_angle && !(out.rho_contour && a.edge);
+    if constexpr (NH == 2) ok = ok && out.var[2] && (a.method != PB_SHG || out.var[3]);
+    return ok;
+}
+
+template <int NH>
+__device__ __forceinline__ void store_pixel(const PixArgs &a, const pb_outputs &out, long long p, const PixOut &o, double I, bool f64, bool lean = false) {
+    if (lean) {
+        reinterpret_cast<float *>(out.var[0])[p] = (float)o.v0;
+        reinterpret_cast<float *>(out.var[1])[p] = (float)o.v1;
+        if constexpr (NH == 2) {
+            reinterpret_cast<float *>(out.var[2])[p] = (float)o.v2;
+            if (a.method == PB_SHG) reinterpret_cast<float *>(out.var[3])[p] = (float)o.v3;
+        }
+        reinterpret_cast<float *>(out.intmap)[p] = (float)o.a0m;
+        out.mask[p] = (uint8_t)o.m;
+        return;
+    }
     store1(out.var[0], p, o.v0, f64);
     store1(out.var[1], p, o.v1, f64);
     if constexpr (NH == 2) {
@@ -262,4 +283,18 @@ __device__ __forceinline__ void store_pixel(const PixArgs &a, const pb_outputs &
         const double e = __ldg(a.edge + p);
         store1(out.rho_contour, p, (pb_finite(o.v0) && pb_finite(e)) ? pb_pymod(o.v0 - e, 180.0) : pb_nan(), f64);
     }
+}
+
+// an invalid pixel on the lean path: NaN maps and a zero mask, no conversions
+template <int NH>
+__device__ __forceinline__ void store_invalid_lean(const PixArgs &a, const pb_outputs &out, long long p) {
+    const float nanf_ = __int_as_float(0x7fc00000);
+    reinterpret_cast<float *>(out.var[0])[p] = nanf_;
+    reinterpret_cast<float *>(out.var[1])[p] = nanf_;
+    if constexpr (NH == 2) {
+        reinterpret_cast<float *>(out.var[2])[p] = nanf_;
+        if (a.method == PB_SHG) reinterpret_cast<float *>(out.var[3])[p] = nanf_;
+    }
+    reinterpret_cast<float *>(out.intmap)[p] = nanf_;
+    out.mask[p] = 0;
 }
