@@ -37,6 +37,7 @@ struct PixArgs {
     const double2 *lut_hy;      // [n-1] (h = g[k+1]-g[k], RN(1/h)) per cell
     const double *hist_edges;   // [n_vars][nbins+1]
     int lut_n;
+    int epi_smem_off;           // per-pixel kernel: byte offset of the stage-B queue / result area in dynamic shared memory (set by the launcher)
     int N, H, W;
     long long P;
     int method;

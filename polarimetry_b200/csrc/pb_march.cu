@@ -31,7 +31,7 @@ bool pb_march_supported(const pb_params *p) {
     if (lw < 2) lw = 2;
     if (32 * (cw + lw) > 1024) return false;
     const int rp = 2 * (((xt + 1) / 2) | 1), fp = (xt % 2) ? xt : xt + 1;
-    const size_t smem = 2 * ((size_t)p->N * (mr + bh - 1) * rp * 2 + 16) + 2 * ((size_t)npos * 4 + 16) + (size_t)(p->N + 1) * mr * fp * 8 + 16 * 1024;
+    const size_t smem = 2 * ((size_t)p->N * march_plane_words(mr + bh - 1, rp / 2, mr) * 4 + 16) + 2 * ((size_t)npos * 4 + 16) + (size_t)(p->N + 1) * mr * fp * 8 + 16 * 1024;
     return smem <= 227 * 1024;
 }
 

@@ -34,7 +34,13 @@ namespace {
 // 32/MR groups of MR rows
 constexpr int PL = 2;      // planes (lines) per chain thread
 constexpr int QMAX = 2;    // tile positions per loader thread
-constexpr int LA = 6;      // angle planes per loader batch
+#ifndef PB_MARCH_LA
+#define PB_MARCH_LA 6
+#endif
+#ifndef PB_MARCH_MAXREG
+#define PB_MARCH_MAXREG 64
+#endif
+constexpr int LA = PB_MARCH_LA;      // angle planes per loader batch
 
 struct MarchArgs {
     int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
@@ -50,12 +56,21 @@ struct MarchArgs {
 #ifndef PB_MARCH_XT_MIN
 #define PB_MARCH_XT_MIN 8          // step width: the smallest multiple of the W window >= this
 #endif
+// Plane pitch of the raw tile in 32-bit words. With fewer than 32 rows per CTA a chain warp holds 32/MR line groups, PL planes
+// apart: the pitch is padded so that the groups fall on disjoint banks (rows are RW words apart, RW odd; the groups must be
+// MR*RW words apart modulo 32).
+__host__ __device__ constexpr int march_plane_words(int rows, int RW, int MR) {
+    int w = rows * RW;
+    if (MR < 32) { while ((PL * w - MR * RW) % 32 != 0) ++w; }
+    return w;
+}
+
 template <int BW> struct StepWidth { static constexpr int M = (PB_MARCH_XT_MIN + BW - 1) / BW; static constexpr int XT = BW * M; };
 template <> struct StepWidth<1> { static constexpr int M = 8; static constexpr int XT = 8; };
 
 // SQ: the H window equals the W window (bh == BW), known at compile time (the common square binning); else bh is a runtime value
 template <typename UT, int NH, int BW, bool SQ, int MR>
-__global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
+__global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSel<NH>::type bs, MarchArgs ma) {
     constexpr int SUBS = 32 / MR;                       // line groups per chain warp
     constexpr int XT = StepWidth<BW>::XT;
     constexpr int FP = (XT % 2) ? XT : XT + 1;          // fbuf row pitch in doubles (odd: conflict-free chain stores)
@@ -74,7 +89,8 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
     const int bh = SQ ? BW : ma.bh;
     const int TR = SQ ? MR + BW - 1 : ma.tile_rows;
     const int NPOS = TR * XT;
-    const int plane_pitch = TR * RP;                     // uint16 per plane of the raw tile
+    constexpr int PPW_SQ = march_plane_words(MR + BW - 1, RW, MR);
+    const int plane_pitch = SQ ? 2 * PPW_SQ : 2 * march_plane_words(ma.tile_rows, RW, MR);   // uint16 per plane of the raw tile
     const int steps = ma.steps;
 
     if (warp >= ma.cw) {
@@ -181,19 +197,7 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
 
         // ---- phase A: the (plane, row) lines advance XT extended positions: tile of step t -> filtered tile
         // one step of a line: q = RN(S1 / bh) [(double)S1 = (2^52 + S1) - 2^52 exactly; H pass skipped if bh <= 1, PP:2944],
-        // tmp += q - ring (W pass, skipped if BW == 1), f = RN(tmp / bw)
-        auto line_step = [&](int c, int j, int S1) -> double {
-            const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
-            const double q = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
-            if constexpr (BW == 1) {
-                return q;
-            } else {
-                const double old = ring[c][j % BW];
-                ring[c][j % BW] = q;
-                tmp[c] = tmp[c] + (q - old);
-                return fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
-            }
-        };
+        // tmp += q - ring (W pass, skipped if BW == 1; scipy's running sum, ring starts at 0.0), f = RN(tmp / bw)
         auto phase_a = [&](int t) {
             const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
             const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
@@ -246,28 +250,50 @@ __global__ void __maxnreg__(64) k_march(PixArgs a, typename BasisSel<NH>::type b
                             if (j0 + jj < XT) cfo[c * (MR * FP) + j0 + jj] = q[jj][c];
                     }
                 }
-            } else {
+            } else if (plane0 <= N) {
+                // the last line group: one image plane (odd N) and / or the total-intensity line (PC:260-264: the same two
+                // passes on the integer sums over the angles). Same staged form, one line at a time -- all the other warps
+                // wait for this one at the end of the phase.
 #pragma unroll
                 for (int c = 0; c < PL; ++c) {
                     const int plane = plane0 + c;
+                    if (plane > N) break;
+                    const bool is_t = plane == N;
+                    const uint16_t *__restrict__ rp = rawb + plane * plane_pitch + crow * RP;
+                    const int *__restrict__ tp = Tb + crow * XT;
                     double *fo = cfo + c * (MR * FP);
-                    if (plane < N) {
-                        const uint16_t *rp = rawb + plane * plane_pitch + crow * RP;
+                    constexpr int JB = (BW == 1) ? 4 : BW;
 #pragma unroll
-                        for (int j = 0; j < XT; ++j) {
-                            int S1 = 0;
-                            for (int dy = 0; dy < bh; ++dy) S1 += (int)rp[dy * RP + j];
-                            fo[j] = line_step(c, j, S1);
-                        }
-                    } else if (plane == N) {
-                        // the total-intensity image (PC:260-264): same two passes on the integer sums over the angles
-                        const int *tp = Tb + crow * XT;
+                    for (int j0 = 0; j0 < XT; j0 += JB) {
+                        double q[JB];
 #pragma unroll
-                        for (int j = 0; j < XT; ++j) {
-                            int S1 = 0;
-                            for (int dy = 0; dy < bh; ++dy) S1 += tp[dy * XT + j];
-                            fo[j] = line_step(c, j, S1);
+                        for (int jj = 0; jj < JB; ++jj) {
+                            if (j0 + jj < XT) {
+                                int S1 = 0;
+                                if constexpr (SQ) {
+#pragma unroll
+                                    for (int dy = 0; dy < BW; ++dy) S1 += is_t ? tp[dy * XT + j0 + jj] : (int)rp[dy * RP + j0 + jj];
+                                } else {
+                                    for (int dy = 0; dy < bh; ++dy) S1 += is_t ? tp[dy * XT + j0 + jj] : (int)rp[dy * RP + j0 + jj];
+                                }
+                                const double u = __hiloint2double(0x43300000, S1) - 4503599627370496.0;
+                                q[jj] = (bh > 1) ? fma(u, ma.bh_hi, u * ma.bh_lo) : u;
+                            }
                         }
+#pragma unroll
+                        for (int jj = 0; jj < JB; ++jj) {
+                            if (j0 + jj < XT) {
+                                if constexpr (BW > 1) {
+                                    const double d = q[jj] - ring[c][(j0 + jj) % BW];
+                                    ring[c][(j0 + jj) % BW] = q[jj];
+                                    tmp[c] = tmp[c] + d;
+                                    q[jj] = fma(tmp[c], ma.bw_hi, tmp[c] * ma.bw_lo);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < JB; ++jj)
+                            if (j0 + jj < XT) fo[j0 + jj] = q[jj];
                     }
                 }
             }
@@ -364,7 +390,7 @@ cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, c
     pb_ddrecip(bh, &ma.bh_hi, &ma.bh_lo);
     pb_ddrecip(BW, &ma.bw_hi, &ma.bw_lo);
     size_t off = hist_bytes(a);
-    ma.raw_bytes = (unsigned)(((size_t)a.N * ma.tile_rows * RP * 2 + 15) & ~(size_t)15);
+    ma.raw_bytes = (unsigned)(((size_t)a.N * march_plane_words(ma.tile_rows, RP / 2, MR) * 4 + 15) & ~(size_t)15);
     ma.T_bytes = (unsigned)(((size_t)npos * 4 + 15) & ~(size_t)15);
     ma.off_raw = (unsigned)off; off += 2 * (size_t)ma.raw_bytes;
     ma.off_T = (unsigned)off; off += 2 * (size_t)ma.T_bytes;
@@ -419,9 +445,12 @@ template <typename UT, int NH>
 cudaError_t launch_nh(const PixArgs &a, const typename BasisSel<NH>::type &bs, const pb_params *p, int n_stacks, cudaStream_t st) {
     int mr = march_rows(a.N);
     if constexpr (std::is_same<UT, uint16_t>::value) {
-        // few stacks (the single-stack drop-in call, the host-buffer pipeline): 32-row CTAs would leave most SMs idle
-        // (2048 rows = 64 CTAs for 148 SMs), so fall to 16 or 8 rows per CTA until the grid covers the machine twice
+        // uint16 stacks with square windows also have the 16- and 8-row variants. 16 rows per CTA (4 CTAs of 8 warps per SM
+        // instead of 2 of 15) measured 2-3 % faster than 32 on full batches; with few stacks (the single-stack drop-in call,
+        // the host-buffer pipeline) go down to 8 rows until the grid covers the machine twice (2048 rows = 64 CTAs of 32
+        // rows for 148 SMs).
         const bool small_ok = p->bin_h == p->bin_w && p->bin_w >= 2 && march_rows_forced() == 0;
+        if (small_ok && mr == 32) mr = 16;
         while (small_ok && mr > 8 && (long long)n_stacks * ((a.H + mr - 1) / mr) < 2 * 148) mr /= 2;
     }
     if (mr == 32) return launch_mr<UT, NH, 32>(a, bs, p, n_stacks, st);

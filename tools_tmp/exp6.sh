@@ -1,0 +1,8 @@
+run() { # lib mr batch extra
+  PB_LIB=$1 PB_MARCH_ROWS=$2 python bench.py --steps 10 --no-cpu --batch $3 $4 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1 mr=$2 b=$3 $4', round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['frac'],4), 'valid', d['config'].get('valid_pixel_fraction'))"
+}
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+run "" 32 32
+run "" 16 32
+run "" 8 32
+run "" 0 1

@@ -1,0 +1,7 @@
+run() { # lib mr batch extra
+  PB_LIB=$1 PB_MARCH_ROWS=$2 python bench.py --steps 10 --no-cpu --batch $3 $4 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$1 mr=$2 b=$3 $4', round(d['value']), round(d['ms_per_step'],3), round(d['roofline']['frac'],4), 'valid', d['config'].get('valid_pixel_fraction'))"
+}
+L=$PWD/polarimetry_b200
+for v in r48 r56 la9 x12 x6; do run $L/libpolarb200_$v.so 16 32; done
+run $L/libpolarb200_la9.so 32 32
+run $L/libpolarb200_x12.so 32 32
