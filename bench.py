@@ -163,7 +163,7 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--bin', type=int, default=int(os.environ.get('PB_BENCH_BIN', '3')))
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('PB_BENCH_BATCH', '16')), help='stacks resident per GPU')
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('PB_BENCH_BATCH', '32')), help='stacks resident per GPU')
     ap.add_argument('--e2e-batch', type=int, default=8)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
