@@ -48,6 +48,9 @@ typedef enum pb_dtype { PB_U8 = 0, PB_U16 = 1, PB_F32 = 2, PB_F64 = 3 } pb_dtype
 #define PB_FLAG_NO_HIST      2u  /* skip in-kernel histograms */
 #define PB_FLAG_EXACT_CHI2   4u  /* always evaluate fit/chi2 in fp64 (disables the certified screening) */
 #define PB_FLAG_FORCE_UNFUSED 8u /* run the separate kernels (field, box filter, per-pixel) even where a fused one exists */
+#define PB_FLAG_PROJECT_ONLY 16u /* 1PF: stop before the disk-cone inversion and write var[0] = Re a2, var[1] = Im a2 (un-normalised,
+                                    PP:2989), intmap = a0 (PP:2987) and mask = the mask of PP:3000 -- the disk-independent part of the
+                                    analysis, input of pb_lut_apply. Implies double maps and no histograms. */
 
 typedef struct pb_ctx pb_ctx;
 
@@ -140,6 +143,13 @@ int pb_stats(pb_ctx *ctx, const void *values_dev, const void *rho_dev, int is_f6
 /* "next" row N2: replaces Stack.compute_dark (PC:266-278): the mean over all angles of the non-zero samples of
  * the size_cell x size_cell cell whose first-angle non-zero mean is smallest. Integer stacks. Synchronises `stream`. */
 int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H, int W, int size_cell, double *dark_host, void *stream);
+
+/* "next" row N1: the disk-dependent tail of the 1PF analysis (PP:2991, PP:3017-3026, PP:3052, PC:340-369) on the
+ * maps written by pb_analyze with PB_FLAG_PROJECT_ONLY: normalisation a2/a0, disk-cone inversion with the CURRENT disk
+ * (pb_set_diskcone), rho rotation / wrap, final mask, intmap, histograms. A calibration sweep over D disks (PP:850-913) projects
+ * every stack once and calls this D times. a0/a2r/a2i: [n_stacks][H,W] double, mask: [n_stacks][H,W] uint8 (DEVICE). */
+int pb_lut_apply(pb_ctx *ctx, const pb_params *params, const double *a0_dev, const double *a2r_dev, const double *a2i_dev,
+                 const uint8_t *mask_dev, int n_stacks, const uint32_t *roi_bits_dev, const pb_outputs *outs_host, void *stream);
 
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */

@@ -422,18 +422,97 @@ class Engine:
                                           C.byref(out), self._stream()), 'pb_compute_dark')
         return float(out.value)
 
+    def project(self, stacks, p: AnalysisParams, rois: Optional[Sequence[dict]] = None, per_roi: bool = False, base_mask=None) -> dict:
+        """The disk-independent part of the 1PF analysis (pre-processing, binning, harmonics, fit / chi2 mask: PP:2953-3000) of
+        stacks [B,N,H,W]: dict of device tensors a0, a2r, a2i (float64 [B,H,W]; a2 un-normalised, PP:2989) and mask (uint8).
+        Input of `lut_apply`; nothing here depends on the disk cone."""
+        if p.method != '1PF':
+            raise ValueError('project / lut_apply: the disk-cone inversion exists for 1PF only (PP:3017)')
+        t = self._to_device(stacks)
+        if t.dim() == 3:
+            t = t[None]
+        B, N, H, W = t.shape
+        self._set_basis(N, p)
+        bits_np, ilows, indices = (None, [], [])
+        roi_dev = None
+        if rois or base_mask is not None:
+            bits_np, ilows, indices = rasterize_rois(rois, (H, W), base_mask)
+            roi_dev = self._to_device(bits_np)
+        self._set_rois(ilows, per_roi)
+        pp = self._params(p, self._dtype_name(t), N, H, W)
+        pp.flags |= _cabi.FLAG_PROJECT_ONLY
+        o = {k: torch.empty((B, H, W), dtype=torch.float64, device=self.device) for k in ('a0', 'a2r', 'a2i')}
+        o['mask'] = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
+        outs = (PbOutputs * B)()
+        for b in range(B):
+            outs[b].var[0] = o['a2r'][b].data_ptr()
+            outs[b].var[1] = o['a2i'][b].data_ptr()
+            outs[b].intmap = o['a0'][b].data_ptr()
+            outs[b].mask = o['mask'][b].data_ptr()
+        self._ck(self.lib.pb_analyze(self._ctx, C.byref(pp), t.data_ptr(), B, _ptr(roi_dev), None, outs, self._stream()), 'pb_analyze')
+        o.update(plan=self.lib.pb_plan(self._ctx, C.byref(pp)).decode(), roi_indices=indices if (per_roi and indices) else [None],
+                 roi_bits=bits_np, ilows=ilows, per_roi=per_roi, shape=(B, N, H, W), src_dtype=self._dtype_name(t), _keep=(t, roi_dev))
+        return o
+
+    def lut_apply(self, proj: dict, p: AnalysisParams, calib: Calibration, want_hist: bool = True, out: Optional[dict] = None) -> dict:
+        """The disk-dependent tail (PP:2991, PP:3017-3026, PP:3052, PC:340-369) on the maps of `project`, with disk cone `calib`:
+        the same dict `analyze_batch` returns (vars, intmap, mask, hist summed over the batch)."""
+        B, N, H, W = proj['shape']
+        names = VAR_NAMES['1PF']
+        self._set_basis(N, p)
+        self._set_calib(p, calib)
+        if want_hist:
+            self._set_hist(p)
+        ng = self._set_rois(proj['ilows'], proj['per_roi'])
+        pp = self._params(p, proj['src_dtype'], N, H, W)
+        if not want_hist:
+            pp.flags |= _cabi.FLAG_NO_HIST
+        mdt = torch.float64 if p.out_dtype == 'float64' else torch.float32
+        o = out if out is not None else {}
+        if 'vars' not in o:
+            o['vars'] = {n: torch.empty((B, H, W), dtype=mdt, device=self.device) for n in names}
+            o['intmap'] = torch.empty((B, H, W), dtype=mdt, device=self.device)
+            o['mask'] = torch.empty((B, H, W), dtype=torch.uint8, device=self.device)
+        if want_hist:
+            if 'hist' not in o:
+                o['hist'] = torch.zeros((1, ng, len(names), p.nbins), dtype=torch.int64, device=self.device)
+            else:
+                o['hist'].zero_()
+        outs = (PbOutputs * B)()
+        for b in range(B):
+            for k, n in enumerate(names):
+                outs[b].var[k] = o['vars'][n][b].data_ptr()
+            outs[b].intmap = o['intmap'][b].data_ptr()
+            outs[b].mask = o['mask'][b].data_ptr()
+            if want_hist:
+                outs[b].hist = o['hist'][0].data_ptr()
+        roi_dev = proj['_keep'][1]
+        self._ck(self.lib.pb_lut_apply(self._ctx, C.byref(pp), proj['a0'].data_ptr(), proj['a2r'].data_ptr(), proj['a2i'].data_ptr(),
+                                       proj['mask'].data_ptr(), B, _ptr(roi_dev), outs, self._stream()), 'pb_lut_apply')
+        o['plan'] = 'lut_apply'
+        o['roi_indices'], o['roi_bits'] = proj['roi_indices'], proj['roi_bits']
+        return o
+
     def calibration_sweep(self, stacks: Sequence, disks: Sequence['Calibration'], p: AnalysisParams, rois: Optional[Sequence[dict]] = None,
-                          per_roi: bool = False, base_mask=None) -> List[dict]:
+                          per_roi: bool = False, base_mask=None, project_once: bool = True) -> List[dict]:
         """The 1PF calibration sweep (PP:850-913, "next" row N1): every disk cone against every stack, one statistics row per
         (disk, stack, ROI) as `analyze_stack(for_calib=True)` returns them (numeric columns of return_vecexcel, PP:2739-2779).
-        The stacks stay resident on the device; only the LUT changes between disks."""
+        Only the LUT changes between disks: each stack is projected ONCE (`project`, everything up to the mask of PP:3000) and
+        the disk-dependent tail (`lut_apply`) runs per disk on the resident maps. project_once=False runs the whole fused
+        analysis per (disk, stack) instead (same rows; kept as the cross-check)."""
         dev_stacks = [self._to_device(s) for s in stacks]
+        sel_rois = [r for r in (rois or []) if r.get('select')] if per_roi else []
+        targets = [(r['indx'], g) for g, r in enumerate(sel_rois)] or [(None, 0)]
+        projs = [self.project(st, p, rois, per_roi, base_mask) for st in dev_stacks] if project_once else None
         rows = []
         for d, cal in enumerate(disks):
             for k, st in enumerate(dev_stacks):
-                res = self.analyze(st, p, cal, rois, per_roi, base_mask, want_hist=False)
-                sel_rois = [r for r in (rois or []) if r.get('select')] if per_roi else []
-                targets = [(r['indx'], g) for g, r in enumerate(sel_rois)] or [(None, 0)]
+                if project_once:
+                    o = self.lut_apply(projs[k], p, cal, want_hist=False)
+                    res = Result([Variable(n, o['vars'][n][0]) for n in VAR_NAMES['1PF']], o['intmap'][0], o['mask'][0], None, {},
+                                 o['roi_bits'], o['plan'])
+                else:
+                    res = self.analyze(st, p, cal, rois, per_roi, base_mask, want_hist=False)
                 for idx, g in targets:
                     row = self.roi_stats(res, p, idx, g)
                     row.update(disk=cal.name or d, stack=k, roi=idx if idx is not None else 1)

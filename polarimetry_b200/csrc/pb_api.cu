@@ -13,6 +13,8 @@
 size_t pb_hist_smem_bytes(int n_vars, int nbins, int n_groups);
 cudaError_t pb_launch_pixel_harm(const PixArgs &a, const Basis2 &bs, int dtype, int n_stacks, cudaStream_t st);
 cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cudaStream_t st);
+cudaError_t pb_launch_lut_apply(const PixArgs &a, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
+                                cudaStream_t st);
 cudaError_t pb_launch_field(const void *v, int dtype, double *out, long long P, int N, double sub, int do_sqrt, int swap12, cudaStream_t st);
 cudaError_t pb_launch_isum(const void *v, int dtype, double *out, long long P, int N, double dark, cudaStream_t st);
 cudaError_t pb_launch_box_y(const double *in, double *out, int planes, int H, int W, int n, cudaStream_t st);
@@ -285,7 +287,8 @@ static int check_params(pb_ctx *ctx, const pb_params *p) {
         if (ctx->invk_rows != (p->method == PB_4POLAR_3D ? 4 : 3)) return fail(ctx, PB_ERR_STATE, "pb_set_invk not called with the K matrix of this method");
     } else {
         if (ctx->basis_n != p->N) return fail(ctx, PB_ERR_STATE, "pb_set_basis not called for this N");
-        if (p->method == PB_1PF && !ctx->lut_dev) return fail(ctx, PB_ERR_STATE, "pb_set_diskcone not called");
+        if (p->method == PB_1PF && !ctx->lut_dev && !(p->flags & PB_FLAG_PROJECT_ONLY)) return fail(ctx, PB_ERR_STATE, "pb_set_diskcone not called");
+        if ((p->flags & PB_FLAG_PROJECT_ONLY) && p->method != PB_1PF) return fail(ctx, PB_ERR_UNSUPPORTED, "PB_FLAG_PROJECT_ONLY: 1PF only");
     }
     return PB_OK;
 }
@@ -302,6 +305,7 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     a.nbins = ctx->nbins > 0 ? ctx->nbins : 1;
     a.n_groups = ctx->n_groups; a.n_rois = ctx->n_rois;
     a.flags = p->flags;
+    if (a.flags & PB_FLAG_PROJECT_ONLY) a.flags |= PB_FLAG_OUT_F64 | PB_FLAG_NO_HIST;
     if (!ctx->basis_orthogonal) a.flags |= PB_FLAG_EXACT_CHI2;
     a.hist_is_rho = ctx->is_rho_bits;
     a.sub = p->dark + p->removed_intensity; a.dark = p->dark;
@@ -471,6 +475,27 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
         if (outs_host[s].intensity) CK(cudaMemcpyAsync(outs_host[s].intensity, Ires, sizeof(double) * P, cudaMemcpyDeviceToDevice, st));
     }
     return ws_release(ctx, st);
+}
+
+int pb_lut_apply(pb_ctx *ctx, const pb_params *p, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
+                 const uint32_t *roi_bits, const pb_outputs *outs_host, void *stream) {
+    int rc = check_params(ctx, p);
+    if (rc) return rc;
+    if (!a0 || !a2r || !a2i || !mask || !outs_host || n_stacks < 1) return fail(ctx, PB_ERR_ARG, "pb_lut_apply: NULL argument");
+    if (p->method != PB_1PF) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_lut_apply: the disk-cone inversion exists for 1PF only (PP:3017)");
+    if (p->flags & PB_FLAG_PROJECT_ONLY) return fail(ctx, PB_ERR_ARG, "pb_lut_apply: PB_FLAG_PROJECT_ONLY belongs to pb_analyze");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    PixArgs a;
+    fill_args(ctx, p, a);
+    a.roi_bits = roi_bits;
+    a.simple = (!roi_bits && ctx->n_rois == 0 && ctx->n_groups == 1) ? 1 : 0;
+    const pb_outputs *od;
+    if ((rc = push_outs(ctx, outs_host, n_stacks, st, &od))) return rc;
+    a.outs = od;
+    CK(pb_launch_lut_apply(a, a0, a2r, a2i, mask, n_stacks, st));
+    ctx->launches++;
+    return PB_OK;
 }
 
 int pb_fit_maps(pb_ctx *ctx, const pb_params *p, const double *field, const uint8_t *mask, double *fit, double *chi2, void *stream) {

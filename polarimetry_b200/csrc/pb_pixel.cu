@@ -424,6 +424,29 @@ __global__ void __launch_bounds__(256) k_pixel_4polar(PixArgs a) {
     if (do_hist) hist_flush(a, hs, out.hist);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Disk-dependent tail of the 1PF analysis on projected maps (calibration sweep): one thread = one pixel.
+__global__ void __launch_bounds__(256) k_lut_apply(PixArgs a, const double *__restrict__ a0, const double *__restrict__ a2r,
+                                                   const double *__restrict__ a2i, const uint8_t *__restrict__ mask) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const pb_outputs out = a.outs[blockIdx.y];
+    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
+    HistSmem hs;
+    hs.cnt = nullptr; hs.edges = nullptr;
+    if (do_hist) hs = hist_setup(a, smem);
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.P) {
+        const long long q = (long long)blockIdx.y * a.P + p;
+        HarmPix h;
+        h.a0 = a0[q]; h.a2r = a2r[q]; h.a2i = a2i[q]; h.a4r = h.a4i = 0.0;
+        h.bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
+        h.m = mask[q] != 0; h.need = false;
+        const PixOut o = harm_stage_b<1>(a, hs, do_hist, h);
+        store_pixel<1>(a, out, p, o, 0.0, a.flags & PB_FLAG_OUT_F64, store_is_lean<1>(a, out));
+    }
+    if (do_hist) hist_flush(a, hs, out.hist);
+}
+
 template <typename T, int NH>
 cudaError_t launch_harm_t(const PixArgs &a_in, const typename BasisSel<NH>::type &bs, int n_stacks, size_t smem, cudaStream_t st) {
     const int threads = 128;
@@ -477,6 +500,18 @@ cudaError_t pb_launch_pixel_harm(const PixArgs &a, const Basis2 &bs, int dtype, 
     }
 #undef PB_DISPATCH
     return cudaErrorInvalidValue;
+}
+
+cudaError_t pb_launch_lut_apply(const PixArgs &a, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
+                                cudaStream_t st) {
+    const size_t smem = pb_hist_smem_bytes(a.n_vars, a.nbins, a.n_groups);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_lut_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((unsigned)((a.P + 255) / 256), n_stacks);
+    k_lut_apply<<<grid, 256, smem, st>>>(a, a0, a2r, a2i, mask);
+    return cudaGetLastError();
 }
 
 cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cudaStream_t st) {

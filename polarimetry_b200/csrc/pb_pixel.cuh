@@ -204,6 +204,12 @@ __device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem 
     o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
     o.m = false;
     if (!h.m) return o;
+    if constexpr (NH == 1) {
+        if (a.flags & PB_FLAG_PROJECT_ONLY) {      // the disk-independent part only (calibration sweep): a2, a0 and the mask of PP:3000
+            o.v0 = h.a2r; o.v1 = h.a2i; o.a0m = h.a0; o.m = true;
+            return o;
+        }
+    }
     const double inv = 1.0 / h.a0;
     double A2 = h.a2r * inv, B2 = h.a2i * inv;
     double v0, v1;

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""N1: calibration sweep D disks x S resident stacks -- project once + D disk-dependent tails against D full fused
+analyses per stack. Device-resident, CUDA-event timing. Prints one JSON line.
+   python tools/sweep_bench.py [--stacks 8] [--disks 8] [--bin 3]"""
+import argparse, json, sys
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from polarimetry_b200 import AnalysisParams, Calibration, Engine, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--stacks', type=int, default=8); ap.add_argument('--disks', type=int, default=8); ap.add_argument('--bin', type=int, default=3)
+a = ap.parse_args()
+H = W = 2048; N = 18
+eng = Engine(0)
+cdir = ROOT / 'tests' / 'golden' / 'calib'
+files = sorted(cdir.glob('Disk_*.npz'))
+disks = []
+for k in range(a.disks):
+    d = np.load(files[k % len(files)])
+    disks.append(Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']), name=f'{files[k % len(files)].stem}#{k}'))
+base = [torch.from_numpy(synth.stack_1pf(H, W, N, seed=500 + k).view(np.int16)) for k in range(min(a.stacks, 4))]
+stacks = torch.empty((a.stacks, N, H, W), dtype=torch.int16, device='cuda')
+for b in range(a.stacks):
+    stacks[b].copy_(base[b % len(base)])
+stacks = stacks.view(torch.uint16)
+p = AnalysisParams(method='1PF', dark=480.0, bins=(a.bin, a.bin), ilow=40000.0, out_dtype='float32')
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+oa, ob = {}, {}
+def full():
+    for cal in disks:
+        eng.analyze_batch(stacks, p, cal, want_intensity=False, out=oa)
+def once():
+    proj = eng.project(stacks, p)
+    for cal in disks:
+        eng.lut_apply(proj, p, cal, out=ob)
+t_full, t_once = timed(full), timed(once)
+# same results for the last disk
+full(); once(); torch.cuda.synchronize()
+same = all(torch.equal(oa['vars'][n].nan_to_num(-1.0), ob['vars'][n].nan_to_num(-1.0)) for n in ('Rho', 'Psi')) and torch.equal(oa['hist'], ob['hist'])
+print(json.dumps({'workload': f'calibration sweep: {a.disks} disk cones x {a.stacks} resident 1PF stacks {H}x{W}x{N} uint16, bin {a.bin}x{a.bin}',
+                  'full_analysis_per_disk_ms': t_full, 'project_once_ms': t_once, 'speedup': t_full / t_once, 'identical_last_disk': bool(same),
+                  'ms_per_disk_stack_full': t_full / (a.disks * a.stacks), 'ms_per_disk_stack_once': t_once / (a.disks * a.stacks)}))
