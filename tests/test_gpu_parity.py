@@ -289,7 +289,10 @@ def test_project_then_lut_apply_equals_fused(eng):
     for x, y in zip(r1, r2):
         assert x.keys() == y.keys()
         for k in x:
-            assert x[k] == y[k] or (isinstance(x[k], float) and np.isnan(x[k]) and np.isnan(y[k])), (k, x[k], y[k])
+            # the maps are bit-identical (above); the moment sums of pb_stats accumulate with atomics, so the statistics are
+            # compared the way the reference prints them (3 decimals, PP:2791-2792)
+            fx, fy = (rs.fmt3(float(z)) if isinstance(z, (float, np.floating)) else z for z in (x[k], y[k]))
+            assert fx == fy, (k, x[k], y[k])
     with pytest.raises(ValueError):
         eng.project(v, AnalysisParams(method='SHG'))
 
