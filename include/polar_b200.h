@@ -151,6 +151,17 @@ int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H,
 int pb_lut_apply(pb_ctx *ctx, const pb_params *params, const double *a0_dev, const double *a2r_dev, const double *a2i_dev,
                  const uint8_t *mask_dev, int n_stacks, const uint32_t *roi_bits_dev, const pb_outputs *outs_host, void *stream);
 
+/* "next" row N4: the boolean-mask gathers of the result writers, on maps the device already holds.
+ *   save_mat (PP:2829-2842): var.values[mask & isfinite(var.values)].astype(float16)       -> filter_dev = NULL, out_f16
+ *   save_csv (PP:2794-2827): xmap/ymap/var.values[mask & isfinite(vars[0].values)]          -> filter_dev = vars[0], out_val, out_index
+ * kept = (sel == NULL || sel[p]) && (roi_bits == NULL || roi_bits[p] & group_bits) && isfinite(filter ? filter[p] : values[p]);
+ * kept elements are written in row-major order (stable compaction): out_f16 = IEEE half of the value (one rounding from fp64,
+ * numpy's astype), out_val = the value itself (same type as values), out_index = linear pixel index p (x = p % W, y = p / W are
+ * the writer's X / Y columns). Any output may be NULL; each must hold up to n elements (or the count of a previous call with the
+ * same filter). *count_host = number kept. Synchronises `stream`. */
+int pb_compact(pb_ctx *ctx, const void *values_dev, const void *filter_dev, int is_f64, const uint8_t *sel_dev, const uint32_t *roi_bits_dev,
+               uint32_t group_bits, long n, void *out_f16_dev, void *out_val_dev, uint32_t *out_index_dev, long *count_host, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------------------ */
 /* number of kernel launches this context has enqueued so far (bench.py's gpu_launches) */
 long pb_launch_count(const pb_ctx *ctx);

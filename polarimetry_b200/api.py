@@ -641,6 +641,87 @@ class Engine:
         out['MeanInt'], out['StdInt'] = s3['mean'], s3['std']
         return out
 
+    # ---- "next" row N4: the result writers' boolean-mask gathers, on the device ---------------------------
+    def compact(self, values, filter=None, sel=None, roi_bits=None, group_bits: int = 0xffffffff, want: Sequence[str] = ('f16',)) -> dict:
+        """`values[keep]` in row-major order with keep = sel & (roi_bits & group_bits) & isfinite(filter or values): dict with
+        any of 'f16' (numpy's astype(float16) of the fp64 value), 'val', 'index' (linear pixel index), and 'count'."""
+        v = self._to_device(values)
+        if v.dtype not in (torch.float32, torch.float64):
+            v = v.to(torch.float64)
+        v = v.contiguous()
+        f = None if filter is None else self._to_device(filter).to(v.dtype).contiguous()
+        s = None if sel is None else self._to_device(sel).to(torch.uint8).contiguous()
+        b = None if roi_bits is None else self._to_device(np.ascontiguousarray(roi_bits, dtype=np.uint32).view(np.int32)).contiguous()
+        n = v.numel()
+        bufs = {'f16': torch.empty(n, dtype=torch.float16, device=self.device) if 'f16' in want else None,
+                'val': torch.empty(n, dtype=v.dtype, device=self.device) if 'val' in want else None,
+                'index': torch.empty(n, dtype=torch.int32, device=self.device) if 'index' in want else None}
+        cnt = C.c_long(0)
+        self._ck(self.lib.pb_compact(self._ctx, v.data_ptr(), _ptr(f), int(v.dtype == torch.float64), _ptr(s), _ptr(b), int(group_bits) & 0xffffffff,
+                                     n, _ptr(bufs['f16']), _ptr(bufs['val']), _ptr(bufs['index']), C.byref(cnt), self._stream()), 'pb_compact')
+        out = {k: t[:cnt.value] for k, t in bufs.items() if t is not None}
+        out['count'] = int(cnt.value)
+        return out
+
+    @staticmethod
+    def _group_bits(res: Result, roi_index: Optional[int], group: int) -> int:
+        # get_slice_roi (PP:2894-2904): one ROI's slice, or any ROI when roi_index is None
+        return (1 << group) if roi_index is not None else 0xffffffff
+
+    def mat_arrays(self, res: Result, roi_index: Optional[int] = None, group: int = 0) -> Dict[str, np.ndarray]:
+        """The arrays save_mat stores (PP:2829-2842): X, Y (uint16 index maps, 0 outside the mask) and, per variable,
+        `var.values[roi & isfinite(var.values)].astype(float16)`, gathered on the device."""
+        H, W = res.mask.shape[-2:]
+        m = res.mask.bool()
+        xx = torch.arange(W, device=m.device, dtype=torch.int32).expand(H, W)
+        yy = torch.arange(H, device=m.device, dtype=torch.int32)[:, None].expand(H, W)
+        zero = torch.zeros((), dtype=torch.int32, device=m.device)
+        d = {'X': torch.where(m, xx, zero).cpu().numpy().astype(np.uint16), 'Y': torch.where(m, yy, zero).cpu().numpy().astype(np.uint16)}
+        gb = self._group_bits(res, roi_index, group)
+        for var in res.vars:
+            d[var.name] = self.compact(var.values, None, None, res.roi_map, gb, want=('f16',))['f16'].cpu().numpy()
+        return d
+
+    def csv_columns(self, res: Result, roi_index: Optional[int] = None, group: int = 0) -> Tuple[List[str], List[np.ndarray]]:
+        """The columns save_csv writes (PP:2794-2811) for the non-contour table: X (uint16), Y (int16) and every non-contour
+        variable under `roi & isfinite(vars[0])`, gathered on the device in row-major order."""
+        W = res.mask.shape[-1]
+        gb = self._group_bits(res, roi_index, group)
+        v0 = res.vars[0].values
+        first = self.compact(v0, None, None, res.roi_map, gb, want=('val', 'index'))
+        idx = first['index'].cpu().numpy().astype(np.int64)
+        names, cols = ['X', 'Y'], [(idx % W).astype(np.uint16), (idx // W).astype(np.int16)]
+        # with edge contours the reference rebinds `filter` to the Rho_contour one before the variable loop (PP:2803-2806)
+        ct = res.get_var('Rho_contour')
+        filt = ct.values if ct is not None else v0
+        for var in res.vars:
+            if '_contour' in var.name:
+                continue
+            col = first['val'] if (var is res.vars[0] and ct is None) else self.compact(var.values, filt, None, res.roi_map, gb, want=('val',))['val']
+            names.append(var.name)
+            cols.append(col.cpu().numpy())
+        return names, cols
+
+    def save_mat(self, res: Result, path, method: str, source: str = '', roi_index: Optional[int] = None, group: int = 0) -> None:
+        """save_mat (PP:2829-2842) on device-resident results."""
+        from datetime import date
+        from scipy.io import savemat
+        d = {'polarimetry': method, 'file': source, 'date': date.today().strftime('%B %d, %Y')}
+        d.update(self.mat_arrays(res, roi_index, group))
+        savemat(str(path), d)
+
+    def save_csv(self, res: Result, path, method: str, source: str = '', roi_index: Optional[int] = None, group: int = 0) -> None:
+        """save_csv (PP:2794-2818, non-contour table) on device-resident results; floats as '%.3f' (PP:2791-2792)."""
+        import csv
+        from datetime import date
+        names, cols = self.csv_columns(res, roi_index, group)
+        fmt = [[f'{x:.3f}' if isinstance(x, float) else x for x in (c.tolist() if c.dtype.kind == 'f' else list(c))] for c in cols]
+        with open(path, 'w', newline='') as f:
+            w = csv.writer(f, delimiter=',', quoting=csv.QUOTE_MINIMAL)
+            w.writerow([f"{method}, file: {source}, date: {date.today().strftime('%B %d %Y')}"])
+            w.writerow(names)
+            w.writerows(zip(*fmt))
+
     def launch_count(self) -> int:
         return int(self.lib.pb_launch_count(self._ctx))
 

@@ -15,6 +15,9 @@ cudaError_t pb_launch_pixel_harm(const PixArgs &a, const Basis2 &bs, int dtype, 
 cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cudaStream_t st);
 cudaError_t pb_launch_lut_apply(const PixArgs &a, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
                                 cudaStream_t st);
+size_t pb_compact_ws_bytes(long long n);
+cudaError_t pb_launch_compact(const void *vals, const void *filt, int is_f64, const uint8_t *sel, const uint32_t *bits, uint32_t group, long long n,
+                              void *ws, void *out_f16, void *out_val, uint32_t *out_index, const unsigned long long **total_dev, cudaStream_t st);
 cudaError_t pb_launch_field(const void *v, int dtype, double *out, long long P, int N, double sub, int do_sqrt, int swap12, cudaStream_t st);
 cudaError_t pb_launch_isum(const void *v, int dtype, double *out, long long P, int N, double dark, cudaStream_t st);
 cudaError_t pb_launch_box_y(const double *in, double *out, int planes, int H, int W, int n, cudaStream_t st);
@@ -555,6 +558,27 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     double var = acc[4] / cnt - md * md;
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
+    return ws_release(ctx, st);
+}
+
+int pb_compact(pb_ctx *ctx, const void *values, const void *filter, int is_f64, const uint8_t *sel, const uint32_t *roi_bits, uint32_t group_bits,
+               long n, void *out_f16, void *out_val, uint32_t *out_index, long *count_host, void *stream) {
+    if (!ctx || !values || !count_host || n < 0) return fail(ctx, PB_ERR_ARG, "pb_compact: bad argument");
+    if (n >= 4294967296L && out_index) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_compact: linear indices are 32-bit");
+    *count_host = 0;
+    if (n == 0) return PB_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ws_reserve(ctx, 4, pb_compact_ws_bytes(n)))) return rc;
+    if ((rc = ws_acquire(ctx, st))) return rc;
+    const unsigned long long *total_dev = nullptr;
+    CK(pb_launch_compact(values, filter, is_f64, sel, roi_bits, group_bits, n, ctx->ws[4], out_f16, out_val, out_index, &total_dev, st));
+    ctx->launches += 3;
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *count_host = (long)total;
     return ws_release(ctx, st);
 }
 

@@ -41,6 +41,9 @@ constexpr int QMAX = 2;    // tile positions per loader thread
 #define PB_MARCH_MAXREG 64
 #endif
 constexpr int LA = PB_MARCH_LA;      // angle planes per loader batch
+#ifndef PB_MARCH_PIPE
+#define PB_MARCH_PIPE 0              // 1: line phase of step t+1 and pixel phase of step t share one barrier interval (double-buffered filtered tile)
+#endif
 
 struct MarchArgs {
     int bh, hh, hw;              // H-window size, its left extent bh/2, W-window left extent bw/2
@@ -51,6 +54,7 @@ struct MarchArgs {
     double bh_hi, bh_lo, bw_hi, bw_lo;   // double-double reciprocals of the bin sizes
     unsigned off_raw, off_T, off_f;      // byte offsets in dynamic shared memory (after the histogram area)
     unsigned raw_bytes, T_bytes;         // size of ONE buffer of the double-buffered raw / T tiles
+    unsigned f_bytes;                    // size of ONE filtered tile (double-buffered when PB_MARCH_PIPE)
 };
 
 #ifndef PB_MARCH_XT_MIN
@@ -114,7 +118,7 @@ __global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSe
             rowoff[q] = pos < NPOS ? (unsigned)pb_reflect(y0 - ma.hh + r, H) * (unsigned)W : 0u;
             if (pos >= NPOS) jj[q] = -1;
         }
-        for (int t = 0; t <= steps; ++t) {
+        for (int t = 0; t <= steps + PB_MARCH_PIPE; ++t) {
             // fill buffer t&1 with the data of step t (t == steps: nothing left, just take part in the barriers)
             if (t < steps) {
                 uint16_t *rawb = reinterpret_cast<uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
@@ -201,7 +205,7 @@ __global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSe
         auto phase_a = [&](int t) {
             const uint16_t *rawb = reinterpret_cast<const uint16_t *>(smem + ma.off_raw + (t & 1) * ma.raw_bytes);
             const int *Tb = reinterpret_cast<const int *>(smem + ma.off_T + (t & 1) * ma.T_bytes);
-            double *const cfo = reinterpret_cast<double *>(smem + ma.off_f) + cfo_off;
+            double *const cfo = reinterpret_cast<double *>(smem + ma.off_f + (PB_MARCH_PIPE ? (t & 1) * ma.f_bytes : 0u)) + cfo_off;
             if (plane0 + PL <= N) {
                 // all PL lines of this thread are image planes. Blocks of JB positions, each in three stages -- all the
                 // shared-memory loads and the independent first-pass quotients, then the (only) sequential part, the two
@@ -300,7 +304,7 @@ __global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSe
         };
         // ---- phase B: the pixels completed by step t
         auto phase_b = [&](int t) {
-            const double *const pfp = reinterpret_cast<const double *>(smem + ma.off_f) + pfp_off;
+            const double *const pfp = reinterpret_cast<const double *>(smem + ma.off_f + (PB_MARCH_PIPE ? (t & 1) * ma.f_bytes : 0u)) + pfp_off;
             const int k = t * XT + pj - (BW - 1);
             if (pix && k >= 0 && k < W) {
                 const long long p = (long long)(y0 + pr) * W + k;
@@ -352,12 +356,23 @@ __global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSe
         };
 
         __syncthreads();                      // tile of step 0 in place
+#if PB_MARCH_PIPE
+        // software pipeline: between two barriers a compute warp filters the lines of step t+1 (into the other filtered tile) and
+        // then finishes the pixels of step t, so that line warps and pixel warps of one CTA overlap; the loader runs two steps ahead
+        // (one instance of each phase in the code: the kernel has to stay inside the instruction cache)
+        for (int t = -1; t < steps; ++t) {
+            if (t + 1 < steps) phase_a(t + 1);
+            if (t >= 0) phase_b(t);
+            __syncthreads();                  // filtered tile of step t+1 complete, raw tile of step t+2 in place
+        }
+#else
         for (int t = 0; t < steps; ++t) {
             phase_a(t);
             asm volatile("bar.sync 1, %0;" ::"r"(ma.cw * 32) : "memory");   // compute warps only: filtered tile of step t complete
             phase_b(t);
             __syncthreads();                  // end-of-step barrier (all warps): filtered tile free again, tile of step t+1 in place
         }
+#endif
     }
     if (do_hist) hist_flush(a, hs, out.hist);
 }
@@ -394,7 +409,8 @@ cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, c
     ma.T_bytes = (unsigned)(((size_t)npos * 4 + 15) & ~(size_t)15);
     ma.off_raw = (unsigned)off; off += 2 * (size_t)ma.raw_bytes;
     ma.off_T = (unsigned)off; off += 2 * (size_t)ma.T_bytes;
-    ma.off_f = (unsigned)off; off += (size_t)(a.N + 1) * MR * FP * 8;
+    ma.f_bytes = (unsigned)((size_t)(a.N + 1) * MR * FP * 8);
+    ma.off_f = (unsigned)off; off += (size_t)ma.f_bytes * (PB_MARCH_PIPE ? 2 : 1);
     if (off > 227 * 1024) return cudaErrorInvalidConfiguration;
     dim3 grid((a.H + MR - 1) / MR, n_stacks);
     cudaError_t e;
