@@ -151,6 +151,12 @@ int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H,
 int pb_lut_apply(pb_ctx *ctx, const pb_params *params, const double *a0_dev, const double *a2r_dev, const double *a2i_dev,
                  const uint8_t *mask_dev, int n_stacks, const uint32_t *roi_bits_dev, const pb_outputs *outs_host, void *stream);
 
+/* "next" row N3: the numeric part of Polarimetry.define_stack (PP:1923-1942) for non-integer TIFF stacks:
+ * out = (65535 * (a - amin(a)) / ptp(a)).astype(uint16) in the array's own precision (PP:1929-1930), min / max over the WHOLE
+ * stack. values_dev: n elements of dtype PB_F32 / PB_F64 (DEVICE), out_dev: n uint16. minmax_host (optional): amin, amax.
+ * A stack holding NaN is refused (the reference's cast is undefined there). Synchronises `stream`. */
+int pb_rescale_stack(pb_ctx *ctx, const void *values_dev, int dtype, long n, uint16_t *out_dev, double *minmax_host, void *stream);
+
 /* "next" row N4: the boolean-mask gathers of the result writers, on maps the device already holds.
  *   save_mat (PP:2829-2842): var.values[mask & isfinite(var.values)].astype(float16)       -> filter_dev = NULL, out_f16
  *   save_csv (PP:2794-2827): xmap/ymap/var.values[mask & isfinite(vars[0].values)]          -> filter_dev = vars[0], out_val, out_index

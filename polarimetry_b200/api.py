@@ -422,6 +422,43 @@ class Engine:
                                           C.byref(out), self._stream()), 'pb_compute_dark')
         return float(out.value)
 
+    def define_stack(self, source, default_dark: Optional[float] = None, size_cell: int = 20) -> dict:
+        """Polarimetry.define_stack (PP:1923-1942, "next" row N3) up to the device: `source` is a multi-page TIFF path (read with
+        cv2.imreadmulti(..., IMREAD_ANYDEPTH) exactly as the reference does) or the pages [N,H,W] themselves. Pages go through a
+        pinned staging buffer to the device; a non-integer stack is rescaled to uint16 there (pb_rescale_stack, PP:1929-1930);
+        dark = default_dark or Stack.compute_dark on the device (PC:266-278, via set_dark PP:2247-2252).
+        Returns dict(values=uint16/uint8 device tensor [N,H,W], nangle, height, width, dark)."""
+        if isinstance(source, (str, Path)):
+            import cv2
+            ok, pages = cv2.imreadmulti(str(source), [], cv2.IMREAD_ANYDEPTH)
+            if not ok or len(pages) == 0:
+                raise FileNotFoundError(f'define_stack: cannot read {source}')
+            a = np.asarray(pages)
+        elif isinstance(source, torch.Tensor):
+            a = source
+        else:
+            a = np.asarray(source)
+        if a.ndim != 3:
+            raise ValueError('define_stack: a stack [nangle, height, width] is required (the reference fails on single pages too, PP:1925-1928)')
+        N, H, W = (int(x) for x in a.shape)
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device).contiguous()
+        else:
+            a = np.ascontiguousarray(a)
+            host = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+            t = host.pin_memory().to(self.device, non_blocking=True)
+            t = t.view(torch.uint16) if a.dtype == np.uint16 else t
+        if t.dtype in (torch.float32, torch.float64):
+            out = torch.empty((N, H, W), dtype=torch.int16, device=self.device).view(torch.uint16)
+            mm = (C.c_double * 2)()
+            self._ck(self.lib.pb_rescale_stack(self._ctx, t.data_ptr(), _cabi.DTYPES[self._dtype_name(t)], t.numel(), out.data_ptr(), mm,
+                                               self._stream()), 'pb_rescale_stack')
+            t = out
+        elif t.dtype not in (torch.uint8, torch.uint16):
+            raise TypeError(f'define_stack: {t.dtype} stacks are not supported (uint8 / uint16 / float32 / float64 TIFF pages)')
+        dark = float(default_dark) if default_dark is not None else self.compute_dark(t, size_cell)
+        return dict(values=t, nangle=N, height=H, width=W, dark=dark)
+
     def project(self, stacks, p: AnalysisParams, rois: Optional[Sequence[dict]] = None, per_roi: bool = False, base_mask=None) -> dict:
         """The disk-independent part of the 1PF analysis (pre-processing, binning, harmonics, fit / chi2 mask: PP:2953-3000) of
         stacks [B,N,H,W]: dict of device tensors a0, a2r, a2i (float64 [B,H,W]; a2 un-normalised, PP:2989) and mask (uint8).

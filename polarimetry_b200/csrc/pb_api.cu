@@ -15,6 +15,7 @@ cudaError_t pb_launch_pixel_harm(const PixArgs &a, const Basis2 &bs, int dtype, 
 cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cudaStream_t st);
 cudaError_t pb_launch_lut_apply(const PixArgs &a, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
                                 cudaStream_t st);
+cudaError_t pb_launch_rescale(const void *a, int is_f64, long long n, unsigned long long *mm_dev, uint16_t *out, cudaStream_t st);
 size_t pb_compact_ws_bytes(long long n);
 cudaError_t pb_launch_compact(const void *vals, const void *filt, int is_f64, const uint8_t *sel, const uint32_t *bits, uint32_t group, long long n,
                               void *ws, void *out_f16, void *out_val, uint32_t *out_index, const unsigned long long **total_dev, cudaStream_t st);
@@ -559,6 +560,37 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
     return ws_release(ctx, st);
+}
+
+int pb_rescale_stack(pb_ctx *ctx, const void *values, int dtype, long n, uint16_t *out, double *minmax_host, void *stream) {
+    if (!ctx || !values || !out || n < 1) return fail(ctx, PB_ERR_ARG, "pb_rescale_stack: bad argument");
+    if (dtype != PB_F32 && dtype != PB_F64) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_rescale_stack: integer stacks are used as they are (PP:1929)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ws_reserve(ctx, 4, 64))) return rc;
+    if ((rc = ws_acquire(ctx, st))) return rc;
+    unsigned long long *mm = reinterpret_cast<unsigned long long *>(ctx->ws[4]);
+    CK(pb_launch_rescale(values, dtype == PB_F64, n, mm, out, st));
+    ctx->launches += 2;
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, mm, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((rc = ws_release(ctx, st))) return rc;
+    if (h[2]) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_rescale_stack: the stack holds NaN (np.amin is NaN: the reference's cast is undefined)");
+    if (minmax_host) {
+        for (int k = 0; k < 2; ++k) {
+            if (dtype == PB_F64) {
+                const unsigned long long u = (h[k] >> 63) ? (h[k] & 0x7fffffffffffffffull) : ~h[k];
+                double d; memcpy(&d, &u, 8); minmax_host[k] = d;
+            } else {
+                const unsigned v = (unsigned)h[k];
+                const unsigned u = (v & 0x80000000u) ? (v & 0x7fffffffu) : ~v;
+                float f; memcpy(&f, &u, 4); minmax_host[k] = f;
+            }
+        }
+    }
+    return PB_OK;
 }
 
 int pb_compact(pb_ctx *ctx, const void *values, const void *filter, int is_f64, const uint8_t *sel, const uint32_t *roi_bits, uint32_t group_bits,

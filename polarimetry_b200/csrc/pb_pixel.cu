@@ -32,7 +32,10 @@ template <> struct RawLoad<uint8_t, 4> {
     __device__ static __forceinline__ unsigned get(const unsigned *w, int k) { return (w[0] >> (8 * k)) & 0xffu; }
 };
 
-constexpr int CH = 6;   // angle planes per software-pipelined chunk
+#ifndef PB_PIXEL_CH
+#define PB_PIXEL_CH 6
+#endif
+constexpr int CH = PB_PIXEL_CH;   // angle planes per software-pipelined chunk
 
 template <typename UT, int PX> struct IntState {
     double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX];
@@ -118,16 +121,14 @@ __device__ __forceinline__ void store4(void *base, long long p, double x0, doubl
 template <typename T, int NH, int PX, int MODE>
 __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixel_harm(PixArgs a, typename BasisSel<NH>::type bs) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const pb_outputs out = a.outs[blockIdx.y];
-    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
-    HistSmem hs;
-    hs.cnt = nullptr; hs.edges = nullptr;
-    if (do_hist) hs = hist_setup(a, smem);
     const long long P = a.P;
     const long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PX;
     const bool active = p0 < P;
     const T *base = reinterpret_cast<const T *>(a.stack) + (long long)blockIdx.y * a.stack_stride + p0;
     double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX], S0d[PX], Sffd[PX], Id[PX];
+    // the projection starts at once: the output pointers and the histogram area are not needed before the epilogue (their
+    // global loads and the set-up barrier would otherwise sit in front of the first stack loads, and the pointers would be
+    // spilled across the loop)
     if (active) {
         const int N = a.N;
         if constexpr (MODE >= 1) {
@@ -221,7 +222,12 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
     unsigned char *rm = reinterpret_cast<unsigned char *>(qidx + cta_px);     // [cta_px] final mask of the queued pixels
     int *qcount = reinterpret_cast<int *>(rm + cta_px);
     if (threadIdx.x == 0) *qcount = 0;
-    __syncthreads();
+    const pb_outputs out = a.outs[blockIdx.y];
+    const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
+    HistSmem hs;
+    hs.cnt = nullptr; hs.edges = nullptr;
+    if (do_hist) hs = hist_setup(a, smem);          // ends with a barrier
+    else __syncthreads();
     const bool f64 = a.flags & PB_FLAG_OUT_F64;
     const int lane = threadIdx.x & 31;
     int qslot[PX];                                                  // queue entry of pixel k of this thread, or -1

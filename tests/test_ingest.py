@@ -1,0 +1,68 @@
+"""raw-stack ingest (Polarimetry.define_stack, PP:1923-1942). Golden = what the UNMODIFIED reference's define_stack
+returned for multi-page TIFFs written here (oracle/make_golden_ingest.py -> tests/golden/ingest.npz)."""
+import numpy as np
+import pytest
+
+from oracle import restate as rs
+from tests import util
+
+KINDS = ('f32', 'f32_small', 'f32_flatmax', 'u16')
+
+
+def golden():
+    return np.load(util.GOLD / 'ingest.npz')
+
+
+@pytest.mark.parametrize('kind', KINDS)
+def test_oracle_define_stack_values(kind):
+    g = golden()
+    out = rs.define_stack_values(g[f'{kind}__in'])
+    assert out.dtype == np.uint16 and np.array_equal(out, g[f'{kind}__out'])
+
+
+def test_oracle_float64_pages():
+    a = golden()['f32__in'].astype(np.float64) * 1.000001
+    out = rs.define_stack_values(a)
+    assert out.dtype == np.uint16 and out.max() == 65535 and out.min() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', KINDS)
+def test_device_define_stack_matches_reference(kind, tmp_path):
+    import cv2
+    from polarimetry_b200 import Engine
+    g = golden()
+    a = g[f'{kind}__in']
+    eng = Engine(0)
+    st = eng.define_stack(a, default_dark=0)
+    assert (st['nangle'], st['height'], st['width']) == a.shape and st['dark'] == 0.0
+    assert np.array_equal(st['values'].cpu().view(dtype=__import__('torch').int16).numpy().view(np.uint16), g[f'{kind}__out'])
+    # the TIFF path: same reader call as the reference (cv2.imreadmulti, IMREAD_ANYDEPTH), dark from the device compute_dark
+    f = tmp_path / f'{kind}.tif'
+    assert cv2.imwritemulti(str(f), list(a))
+    st2 = eng.define_stack(f)
+    vals = st2['values'].cpu().view(dtype=__import__('torch').int16).numpy().view(np.uint16)
+    assert np.array_equal(vals, g[f'{kind}__out'])
+    assert st2['dark'] == rs.compute_dark(g[f'{kind}__out'])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_device_rescale_large_and_float64():
+    """2048x2048x6 float32 and float64 stacks against the NumPy statement (bit-exact), NaN refused."""
+    import torch
+    from polarimetry_b200 import Engine
+    eng = Engine(0)
+    rng = np.random.default_rng(3)
+    for dt in (np.float32, np.float64):
+        a = (rng.gamma(2.0, 700.0, size=(6, 1024, 2048)) - 250.0).astype(dt)
+        st = eng.define_stack(a, default_dark=0)
+        got = st['values'].cpu().view(dtype=torch.int16).numpy().view(np.uint16)
+        assert np.array_equal(got, rs.define_stack_values(a))
+    a = np.ones((2, 8, 8), dtype=np.float32)
+    a[1, 3, 3] = np.nan
+    with pytest.raises(RuntimeError):
+        eng.define_stack(a, default_dark=0)
+    with pytest.raises(ValueError):
+        eng.define_stack(np.ones((8, 8), dtype=np.float32))
+    eng.close()
