@@ -338,7 +338,9 @@ __global__ void __maxnreg__(PB_MARCH_MAXREG) k_march(PixArgs a, typename BasisSe
                         }
                         Sff = fma(f, f, Sff);                    // screening only
                     }
-                    HarmPix hp = harm_stage_a<NH>(a, p, S0, Sc, Ss, Sc4, Ss4, Sff, I);
+                    // the threshold / ROI test is `cand` (above): stage A proper
+                    const uint32_t bits = (a.simple || !a.roi_bits) ? 1u : __ldg(a.roi_bits + p);
+                    HarmPix hp = harm_stage_a_core<NH>(a, bits, S0, Sc, Ss, Sc4, Ss4, Sff);
                     if (hp.need) {
                         ExactAcc ex;
                         ex.init();

@@ -33,7 +33,7 @@ template <> struct RawLoad<uint8_t, 4> {
 };
 
 #ifndef PB_PIXEL_CH
-#define PB_PIXEL_CH 6
+#define PB_PIXEL_CH 3
 #endif
 constexpr int CH = PB_PIXEL_CH;   // angle planes per software-pipelined chunk
 
@@ -205,18 +205,18 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
             }
         }
     }
-    // ---- Epilogue in two stages.
-    // Stage A (owner thread, its PX pixels): threshold / ROI test, a0 / a2 / a4, the certified fit/chi2 screening and, for the
-    // rare undecided pixel, the reference's fp64 loop (PP:2987-3000). Pixels that are still candidates are pushed into a
+    // ---- Epilogue.
+    // Owner thread (its PX pixels): only the threshold / ROI test (PP:2891). Pixels that pass are pushed, with their sums, into a
     // per-CTA queue in shared memory.
-    // Stage B (any thread, one queued pixel at a time): normalisation, disk-cone LUT or 4-harmonic outputs, histograms
-    // (PP:3017-3053, PC:340-369). On thresholded images only a fraction of the pixels reaches stage B: taking them from the
-    // queue keeps every lane of the warps that run it busy, instead of every warp paying for its few valid lanes.
+    // Dense pass (any thread, one queued pixel at a time): a0 / a2 / a4, the certified fit/chi2 screening and, for the rare
+    // undecided pixel, the reference's fp64 loop (PP:2987-3000); normalisation, disk-cone LUT or 4-harmonic outputs, histograms
+    // (PP:3017-3053, PC:340-369). On thresholded images only a fraction of the pixels gets here: taking them from the queue
+    // keeps every lane of the warps that run it busy, instead of every warp paying for its few valid lanes.
     // The owner threads then write their PX consecutive pixels with vector stores.
-    constexpr int NQ = 1 + 2 * NH;                                  // a0, a2r, a2i (, a4r, a4i)
+    constexpr int NQ = 2 + 2 * NH;                                  // S0, Sc, Ss (, Sc4, Ss4), Sff
     constexpr int NR = 2 * NH + 1;                                  // v0, v1 (, v2, v3), a0m
     const int cta_px = blockDim.x * PX;
-    static_assert(NQ == NR, "stage B writes its results over the queue entry it consumed");
+    static_assert(NR <= NQ, "the dense pass writes its results over the queue entry it consumed");
     double *qv = reinterpret_cast<double *>(smem + a.epi_smem_off);            // [NQ][cta_px] queue entries, then their results
     unsigned short *qidx = reinterpret_cast<unsigned short *>(qv + NQ * cta_px);   // [cta_px] local pixel of each queue entry
     unsigned char *rm = reinterpret_cast<unsigned char *>(qidx + cta_px);     // [cta_px] final mask of the queued pixels
@@ -232,69 +232,56 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
     const int lane = threadIdx.x & 31;
     int qslot[PX];                                                  // queue entry of pixel k of this thread, or -1
     double Iv[PX];
-    {
-        HarmPix hp[PX];
-        bool any_need = false;
 #pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            Iv[k] = 0.0;
-            hp[k].m = false; hp[k].need = false;
-            if (active) {
-                Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
-                hp[k] = harm_stage_a<NH>(a, p0 + k, S0d[k], Sc[k], Ss[k], Sc4[k], Ss4[k], Sffd[k], Iv[k]);
-                any_need |= hp[k].need;
-            }
+    for (int k = 0; k < PX; ++k) {
+        Iv[k] = 0.0;
+        bool m = false;
+        if (active) {
+            uint32_t bits;
+            Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
+            m = harm_threshold(a, p0 + k, Iv[k], bits);
         }
-        if (any_need) {
-            // rare path: the reference's fp64 fit/chi2 loop for the undecided pixels of this thread (stack re-read, L1/L2 hits)
-            ExactAcc ex[PX];
-#pragma unroll
-            for (int k = 0; k < PX; ++k) ex[k].init();
-            for (int i = 0; i < a.N; ++i) {
-                double v[PX];
-                VecLoad<T, PX>::ld(base + (long long)i * P, v);
-                double c4 = 0.0, s4 = 0.0;
-                if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
-#pragma unroll
-                for (int k = 0; k < PX; ++k) {
-                    double f = v[k];
-                    if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
-                    ex[k].template step<NH>(hp[k], f, bs.c2[i], bs.s2[i], c4, s4);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PX; ++k)
-                if (hp[k].need) hp[k].m = ex[k].decide(a);
-        }
-#pragma unroll
-        for (int k = 0; k < PX; ++k) {
-            const bool m = hp[k].m;
-            qslot[k] = -1;
-            const unsigned ball = __ballot_sync(0xffffffffu, m);
-            int e0 = 0;
-            if (lane == 0 && ball) e0 = atomicAdd(qcount, __popc(ball));
-            e0 = __shfl_sync(0xffffffffu, e0, 0);
-            if (m) {
-                const int e = e0 + __popc(ball & ((1u << lane) - 1u));
-                qv[e] = hp[k].a0; qv[cta_px + e] = hp[k].a2r; qv[2 * cta_px + e] = hp[k].a2i;
-                if constexpr (NH == 2) { qv[3 * cta_px + e] = hp[k].a4r; qv[4 * cta_px + e] = hp[k].a4i; }
-                qidx[e] = (unsigned short)(threadIdx.x * PX + k);
-                qslot[k] = e;
-            }
+        qslot[k] = -1;
+        const unsigned ball = __ballot_sync(0xffffffffu, m);
+        int e0 = 0;
+        if (lane == 0 && ball) e0 = atomicAdd(qcount, __popc(ball));
+        e0 = __shfl_sync(0xffffffffu, e0, 0);
+        if (m) {
+            const int e = e0 + __popc(ball & ((1u << lane) - 1u));
+            qv[e] = S0d[k]; qv[cta_px + e] = Sc[k]; qv[2 * cta_px + e] = Ss[k];
+            if constexpr (NH == 2) { qv[3 * cta_px + e] = Sc4[k]; qv[4 * cta_px + e] = Ss4[k]; }
+            qv[(NQ - 1) * cta_px + e] = Sffd[k];
+            qidx[e] = (unsigned short)(threadIdx.x * PX + k);
+            qslot[k] = e;
         }
     }
     __syncthreads();
     {
         const int qn = *qcount;
         const long long pcta = (long long)blockIdx.x * cta_px;
+        const T *cta_stack = reinterpret_cast<const T *>(a.stack) + (long long)blockIdx.y * a.stack_stride + pcta;
         for (int e = threadIdx.x; e < qn; e += blockDim.x) {
-            HarmPix h;
-            h.a0 = qv[e]; h.a2r = qv[cta_px + e]; h.a2i = qv[2 * cta_px + e];
-            h.a4r = h.a4i = 0.0;
-            if constexpr (NH == 2) { h.a4r = qv[3 * cta_px + e]; h.a4i = qv[4 * cta_px + e]; }
             const int lp = qidx[e];
-            h.bits = (a.simple || !a.roi_bits) ? 1u : __ldg(a.roi_bits + pcta + lp);
-            h.m = true; h.need = false;
+            const uint32_t bits = (a.simple || !a.roi_bits) ? 1u : __ldg(a.roi_bits + pcta + lp);
+            double c4s = 0.0, s4s = 0.0;
+            if constexpr (NH == 2) { c4s = qv[3 * cta_px + e]; s4s = qv[4 * cta_px + e]; }
+            HarmPix h = harm_stage_a_core<NH>(a, bits, qv[e], qv[cta_px + e], qv[2 * cta_px + e], c4s, s4s, qv[(NQ - 1) * cta_px + e]);
+            if (h.need) {
+                // rare path: the reference's fp64 fit/chi2 loop for an undecided pixel (stack re-read, L1/L2 hits)
+                ExactAcc ex;
+                ex.init();
+                const T *pp = cta_stack + lp;
+#pragma unroll 1
+                for (int i = 0; i < a.N; ++i) {
+                    double f = (double)__ldg(pp + (long long)i * P);
+                    if (!a.from_field) { f = pb_max0(f - a.sub); if (a.do_sqrt) f = sqrt(f); }
+                    double c4 = 0.0, s4 = 0.0;
+                    if constexpr (NH == 2) { c4 = bs.c4[i]; s4 = bs.s4[i]; }
+                    ex.template step<NH>(h, f, bs.c2[i], bs.s2[i], c4, s4);
+                }
+                h.m = ex.decide(a);
+                h.need = false;
+            }
             const PixOut o = harm_stage_b<NH>(a, hs, do_hist, h);
             qv[e] = o.v0; qv[cta_px + e] = o.v1;
             if constexpr (NH == 2) { qv[2 * cta_px + e] = o.v2; qv[3 * cta_px + e] = o.v3; }
@@ -459,11 +446,11 @@ cudaError_t launch_harm_t(const PixArgs &a_in, const typename BasisSel<NH>::type
     PixArgs a = a_in;
     // PX = 4 needs every plane (and every stack) to start on a 4-element boundary
     const bool vec = (a.P % 4 == 0) && (a.stack_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.stack) % (4 * sizeof(T))) == 0);
-    // stage-B queue (results overwrite the entries) behind the histograms: per pixel of the CTA 1 + 2 NH doubles, a 16-bit
+    // epilogue queue (results overwrite the entries) behind the histograms: per pixel of the CTA 2 + 2 NH doubles, a 16-bit
     // index and a mask byte; then the queue counter
     smem = (smem + 15) & ~(size_t)15;
     a.epi_smem_off = (int)smem;
-    smem += (size_t)threads * (vec ? 4 : 1) * (8 * (1 + 2 * NH) + 3) + 16;
+    smem += (size_t)threads * (vec ? 4 : 1) * (8 * (2 + 2 * NH) + 3) + 16;
     // integer fast path: integer stack, integer-valued offsets that fit the element range, no sqrt
     constexpr bool is_int = std::is_same<T, uint8_t>::value || std::is_same<T, uint16_t>::value;
     const bool fast = is_int && !a.from_field && !a.do_sqrt && !a.intensity_in && a.sub == floor(a.sub) && a.dark == floor(a.dark) &&

@@ -144,23 +144,27 @@ struct ExactAcc {
     }
 };
 
-// Stage A (PP:2987-3000 decisions): threshold / ROI test, a0 / a2 / a4, certified screening of
+// threshold / ROI part of the mask (PP:2891 + PP:2967) for one pixel; `bits` receives the pixel's ROI bit set
+__device__ __forceinline__ bool harm_threshold(const PixArgs &a, long long p, double I, uint32_t &bits) {
+    if (a.simple) {                                            // whole image, one threshold (PP:2875-2876)
+        bits = 1u;
+        return I >= a.roi_ilow[0];
+    }
+    bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
+    return a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, bits, I);
+}
+
+// Stage A (PP:2987-3000 decisions) for a pixel that passed the threshold / ROI test: a0 / a2 / a4, certified screening of
 // (all fit_i > 0) & (chi2 <= thr) & (chi2 > 0).
-//   S0,Sc,Ss,(Sc4,Ss4): the sequential sums of PP:2987-2994 ; Sff: sum f^2 (screening only) ; I: threshold image value
+//   S0,Sc,Ss,(Sc4,Ss4): the sequential sums of PP:2987-2994 ; Sff: sum f^2 (screening only)
 template <int NH>
-__device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, double S0, double Sc, double Ss, double Sc4, double Ss4,
-                                                double Sff, double I) {
+__device__ __forceinline__ HarmPix harm_stage_a_core(const PixArgs &a, uint32_t bits, double S0, double Sc, double Ss, double Sc4, double Ss4,
+                                                     double Sff) {
     HarmPix h;
     h.a0 = pb_nan(); h.a2r = h.a2i = h.a4r = h.a4i = 0.0;
     h.need = false;
-    if (a.simple) {                                            // whole image, one threshold (PP:2875-2876)
-        h.bits = 1u;
-        h.m = I >= a.roi_ilow[0];
-    } else {
-        h.bits = a.roi_bits ? __ldg(a.roi_bits + p) : 1u;
-        h.m = a.mask_in ? (__ldg(a.mask_in + p) != 0) : roi_pass(a, h.bits, I);
-    }
-    if (!h.m) return h;
+    h.bits = bits;
+    h.m = true;
     // S0 / N correctly rounded without a division: fma(S0, rhi, S0*rlo) with (rhi, rlo) the double-double 1/N
     // (tests/test_shortcuts.py; x/N is never within 2^-60 of a rounding boundary, the approximation error is 2^-105)
     const double a0 = fma(S0, a.invN_hi, S0 * a.invN_lo);
@@ -195,6 +199,20 @@ __device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, d
         }
     }
     return h;
+}
+
+// threshold / ROI test + stage A (the form the row-march kernel and the one-pixel-per-thread paths use)
+template <int NH>
+__device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, double S0, double Sc, double Ss, double Sc4, double Ss4,
+                                                double Sff, double I) {
+    uint32_t bits;
+    if (!harm_threshold(a, p, I, bits)) {
+        HarmPix h;
+        h.a0 = pb_nan(); h.a2r = h.a2i = h.a4r = h.a4i = 0.0;
+        h.need = false; h.m = false; h.bits = bits;
+        return h;
+    }
+    return harm_stage_a_core<NH>(a, bits, S0, Sc, Ss, Sc4, Ss4, Sff);
 }
 
 // Stage B (PP:3017-3040 outputs, PP:3052, histograms) for a pixel whose fit/chi2 decision is h.m.
