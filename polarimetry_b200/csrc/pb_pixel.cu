@@ -33,9 +33,9 @@ template <> struct RawLoad<uint8_t, 4> {
 };
 
 #ifndef PB_PIXEL_CH
-#define PB_PIXEL_CH 3
+#define PB_PIXEL_CH 6
 #endif
-constexpr int CH = PB_PIXEL_CH;   // angle planes per software-pipelined chunk
+constexpr int CH = PB_PIXEL_CH;   // angle planes in flight per thread (depth of the rotating load queue)
 
 template <typename UT, int PX> struct IntState {
     double Sc[PX], Ss[PX], Sc4[PX], Ss4[PX];
@@ -43,44 +43,9 @@ template <typename UT, int PX> struct IntState {
     unsigned long long Sff[PX];
 };
 
-template <typename UT, int PX, bool FULL>
-__device__ __forceinline__ void load_chunk(const UT *&ptr, long long P, unsigned (&buf)[CH][RawLoad<UT, PX>::WORDS], int cnt) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-        if (FULL || j < cnt) { RawLoad<UT, PX>::ld(ptr, buf[j]); ptr += P; }
-}
-
-// one chunk of the projection on the integer fast path: per pixel-angle one unpack, one fused subtract/clamp,
-// integer S0 and sum f^2, and per harmonic component ONE DFMA (the rounded product RN(f c) = fma(2^52+f, c, -(2^52 c)))
-// plus ONE DADD (the reference's separately rounded accumulation, PP:2989 / einsum).
-template <typename UT, int NH, int PX, bool FULL, bool SEP, typename Basis>
-__device__ __forceinline__ void compute_chunk(IntState<UT, PX> &s, const unsigned (&buf)[CH][RawLoad<UT, PX>::WORDS], const Basis &bs,
-                                              int i0, int cnt, int isub, int idark) {
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-        if (FULL || j < cnt) {
-            const int i = i0 + j;
-            const double c2 = bs.c2[i], s2 = bs.s2[i], kc2 = bs.kc2[i], ks2 = bs.ks2[i];
-#pragma unroll
-            for (int k = 0; k < PX; ++k) {
-                const int v = (int)RawLoad<UT, PX>::get(buf[j], k);
-                const int f = max(v - isub, 0);
-                if constexpr (SEP) s.Ii[k] += (unsigned)max(v - idark, 0);
-                s.S0[k] += (unsigned)f;
-                s.Sff[k] += (unsigned long long)((unsigned)f) * (unsigned)f;
-                const double X = __hiloint2double(0x43300000, f);   // 2^52 + f, exact
-                s.Sc[k] = s.Sc[k] + fma(X, c2, kc2);
-                s.Ss[k] = s.Ss[k] + fma(X, s2, ks2);
-                if constexpr (NH == 2) {
-                    s.Sc4[k] = s.Sc4[k] + fma(X, bs.c4[i], bs.kc4[i]);
-                    s.Ss4[k] = s.Ss4[k] + fma(X, bs.s4[i], bs.ks4[i]);
-                }
-            }
-        }
-    }
-}
-
-// one plane (tail of the angle loop)
+// one plane of the projection on the integer fast path: per pixel-angle one unpack, one fused subtract/clamp, integer S0 and
+// sum f^2, and per harmonic component ONE DFMA (the rounded product RN(f c) = fma(2^52+f, c, -(2^52 c))) plus ONE DADD (the
+// reference's separately rounded accumulation, PP:2989 / einsum)
 template <typename UT, int NH, int PX, bool SEP, typename Basis>
 __device__ __forceinline__ void compute_one(IntState<UT, PX> &s, const unsigned *w, const Basis &bs, int i, int isub, int idark) {
     const double c2 = bs.c2[i], s2 = bs.s2[i], kc2 = bs.kc2[i], ks2 = bs.ks2[i];
@@ -139,31 +104,24 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
             IntState<UT, PX> s;
 #pragma unroll
             for (int k = 0; k < PX; ++k) { s.Sc[k] = s.Ss[k] = s.Sc4[k] = s.Ss4[k] = 0.0; s.S0[k] = s.Ii[k] = 0u; s.Sff[k] = 0ull; }
-            unsigned A[CH][RawLoad<UT, PX>::WORDS], B[CH][RawLoad<UT, PX>::WORDS];
-            // full chunks of CH planes, ping-pong: A holds planes [i, i+CH), B is loaded while A is consumed, and vice versa.
-            // (Only the unpredicated chunk code is instantiated -- twice -- to keep the kernel inside the instruction cache;
-            // the N % CH remaining planes go through a small rolled loop.)
-            const int nfull = N / CH;
+            // rotating register queue of CH planes: plane i is consumed from slot i % CH and the slot is at once reloaded with
+            // plane i + CH, so CH loads stay in flight with CH (not 2 CH) buffers -- with ping-pong buffers the compiler ran out
+            // of registers and spilled the data of loads still in flight, which made every prefetch synchronous
+            unsigned buf[CH][RawLoad<UT, PX>::WORDS];
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+                if (j < N) { RawLoad<UT, PX>::ld(ptr, buf[j]); ptr += P; }
             int i = 0;
-            if (nfull > 0) {
-                load_chunk<UT, PX, true>(ptr, P, A, CH);
-                for (int c = 0; c < nfull; c += 2) {
-                    if (c + 1 < nfull) load_chunk<UT, PX, true>(ptr, P, B, CH);
-                    compute_chunk<UT, NH, PX, true, SEP>(s, A, bs, i, CH, isub, idark);
-                    i += CH;
-                    if (c + 1 >= nfull) break;
-                    if (c + 2 < nfull) load_chunk<UT, PX, true>(ptr, P, A, CH);
-                    compute_chunk<UT, NH, PX, true, SEP>(s, B, bs, i, CH, isub, idark);
-                    i += CH;
+            for (; i + CH <= N; i += CH) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    compute_one<UT, NH, PX, SEP>(s, buf[j], bs, i + j, isub, idark);
+                    if (i + j + CH < N) { RawLoad<UT, PX>::ld(ptr, buf[j]); ptr += P; }
                 }
             }
-#pragma unroll 1
-            for (; i < N; ++i) {
-                unsigned w[1][RawLoad<UT, PX>::WORDS];
-                RawLoad<UT, PX>::ld(ptr, w[0]);
-                ptr += P;
-                compute_one<UT, NH, PX, SEP>(s, w[0], bs, i, isub, idark);
-            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j)                               // the N % CH planes left in the queue
+                if (i + j < N) compute_one<UT, NH, PX, SEP>(s, buf[j], bs, i + j, isub, idark);
 #pragma unroll
             for (int k = 0; k < PX; ++k) {
                 Sc[k] = s.Sc[k]; Ss[k] = s.Ss[k]; Sc4[k] = s.Sc4[k]; Ss4[k] = s.Ss4[k];
@@ -232,28 +190,55 @@ __global__ void __launch_bounds__(128, NH == 1 ? PB_PIXEL_MIN_BLOCKS : 5) k_pixe
     const int lane = threadIdx.x & 31;
     int qslot[PX];                                                  // queue entry of pixel k of this thread, or -1
     double Iv[PX];
+    // queue slots. AGG (4-harmonic kernels, 96 registers): one shared-memory atomic per warp for all its PX x 32 pixels, entries
+    // numbered pixel slot by pixel slot; otherwise (1PF, 64 registers: the extra live flags cost spills in the projection loop,
+    // measured 843 -> 694 k Mpx-angles/s) one atomic per pixel slot.
+    constexpr bool AGG = NH == 2;
+    bool pm[PX];
+    unsigned ball[PX];
+    int e0 = 0;
+    if constexpr (AGG) {
+        int wcount = 0;
+#pragma unroll
+        for (int k = 0; k < PX; ++k) {
+            Iv[k] = 0.0;
+            pm[k] = false;
+            if (active) {
+                uint32_t bits;
+                Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
+                pm[k] = harm_threshold(a, p0 + k, Iv[k], bits);
+            }
+            ball[k] = __ballot_sync(0xffffffffu, pm[k]);
+            wcount += __popc(ball[k]);
+        }
+        if (lane == 0 && wcount) e0 = atomicAdd(qcount, wcount);
+        e0 = __shfl_sync(0xffffffffu, e0, 0);
+    }
 #pragma unroll
     for (int k = 0; k < PX; ++k) {
-        Iv[k] = 0.0;
-        bool m = false;
-        if (active) {
-            uint32_t bits;
-            Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
-            m = harm_threshold(a, p0 + k, Iv[k], bits);
+        if constexpr (!AGG) {
+            Iv[k] = 0.0;
+            pm[k] = false;
+            if (active) {
+                uint32_t bits;
+                Iv[k] = a.intensity_in ? __ldg(a.intensity_in + p0 + k) : Id[k];
+                pm[k] = harm_threshold(a, p0 + k, Iv[k], bits);
+            }
+            ball[k] = __ballot_sync(0xffffffffu, pm[k]);
+            e0 = 0;
+            if (lane == 0 && ball[k]) e0 = atomicAdd(qcount, __popc(ball[k]));
+            e0 = __shfl_sync(0xffffffffu, e0, 0);
         }
         qslot[k] = -1;
-        const unsigned ball = __ballot_sync(0xffffffffu, m);
-        int e0 = 0;
-        if (lane == 0 && ball) e0 = atomicAdd(qcount, __popc(ball));
-        e0 = __shfl_sync(0xffffffffu, e0, 0);
-        if (m) {
-            const int e = e0 + __popc(ball & ((1u << lane) - 1u));
+        if (pm[k]) {
+            const int e = e0 + __popc(ball[k] & ((1u << lane) - 1u));
             qv[e] = S0d[k]; qv[cta_px + e] = Sc[k]; qv[2 * cta_px + e] = Ss[k];
             if constexpr (NH == 2) { qv[3 * cta_px + e] = Sc4[k]; qv[4 * cta_px + e] = Ss4[k]; }
             qv[(NQ - 1) * cta_px + e] = Sffd[k];
             qidx[e] = (unsigned short)(threadIdx.x * PX + k);
             qslot[k] = e;
         }
+        if constexpr (AGG) e0 += __popc(ball[k]);
     }
     __syncthreads();
     {
