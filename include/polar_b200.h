@@ -151,6 +151,10 @@ int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H,
 int pb_lut_apply(pb_ctx *ctx, const pb_params *params, const double *a0_dev, const double *a2r_dev, const double *a2i_dev,
                  const uint8_t *mask_dev, int n_stacks, const uint32_t *roi_bits_dev, const pb_outputs *outs_host, void *stream);
 
+/* Layout conversion at the boundary: an angle-minor stack [H,W,N] (the N samples of a pixel contiguous) to the
+ * reference's angle-major [N,H,W] (PP:1926), which every other entry point takes. Out of place, same dtype, N <= 128. */
+int pb_stack_from_hwn(pb_ctx *ctx, const void *stack_hwn_dev, int dtype, int N, int H, int W, void *stack_nhw_dev, void *stream);
+
 /* "next" row N3: the numeric part of Polarimetry.define_stack (PP:1923-1942) for non-integer TIFF stacks:
  * out = (65535 * (a - amin(a)) / ptp(a)).astype(uint16) in the array's own precision (PP:1929-1930), min / max over the WHOLE
  * stack. values_dev: n elements of dtype PB_F32 / PB_F64 (DEVICE), out_dev: n uint16. minmax_host (optional): amin, amax.

@@ -50,6 +50,7 @@ EXPORTS = {
     'pb_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     'pb_compute_dark': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     'pb_lut_apply': (C.c_int, [C.c_void_p, C.POINTER(PbParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PbOutputs), C.c_void_p]),
+    'pb_stack_from_hwn': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'pb_rescale_stack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     'pb_compact': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.POINTER(C.c_long), C.c_void_p]),

@@ -422,6 +422,23 @@ class Engine:
                                           C.byref(out), self._stream()), 'pb_compute_dark')
         return float(out.value)
 
+    def from_hwn(self, stack_hwn) -> torch.Tensor:
+        """Angle-minor stack(s) [..., H, W, N] (the N samples of a pixel contiguous) -> the reference's angle-major [..., N, H, W]
+        (PP:1926) on the device, same dtype; every analysis entry point takes the result."""
+        t = self._to_device(stack_hwn)
+        if t.dim() < 3:
+            raise ValueError('from_hwn: [H, W, N] or [B, H, W, N] required')
+        lead = t.shape[:-3]
+        H, W, N = (int(x) for x in t.shape[-3:])
+        src = t.reshape(-1, H, W, N)
+        dst = torch.empty((src.shape[0], N, H, W), dtype=torch.int16 if t.dtype == torch.uint16 else t.dtype, device=self.device)
+        if t.dtype == torch.uint16:
+            dst = dst.view(torch.uint16)
+        for b in range(src.shape[0]):
+            self._ck(self.lib.pb_stack_from_hwn(self._ctx, src[b].data_ptr(), _cabi.DTYPES[self._dtype_name(t)], N, H, W, dst[b].data_ptr(),
+                                                self._stream()), 'pb_stack_from_hwn')
+        return dst.reshape(*lead, N, H, W)
+
     def define_stack(self, source, default_dark: Optional[float] = None, size_cell: int = 20) -> dict:
         """Polarimetry.define_stack (PP:1923-1942, "next" row N3) up to the device: `source` is a multi-page TIFF path (read with
         cv2.imreadmulti(..., IMREAD_ANYDEPTH) exactly as the reference does) or the pages [N,H,W] themselves. Pages go through a

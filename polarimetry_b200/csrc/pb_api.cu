@@ -16,6 +16,7 @@ cudaError_t pb_launch_pixel_4polar(const PixArgs &a, int dtype, int n_stacks, cu
 cudaError_t pb_launch_lut_apply(const PixArgs &a, const double *a0, const double *a2r, const double *a2i, const uint8_t *mask, int n_stacks,
                                 cudaStream_t st);
 cudaError_t pb_launch_rescale(const void *a, int is_f64, long long n, unsigned long long *mm_dev, uint16_t *out, cudaStream_t st);
+cudaError_t pb_launch_hwn_to_nhw(const void *in, void *out, int elem_bytes, long long P, int N, cudaStream_t st);
 size_t pb_compact_ws_bytes(long long n);
 cudaError_t pb_launch_compact(const void *vals, const void *filt, int is_f64, const uint8_t *sel, const uint32_t *bits, uint32_t group, long long n,
                               void *ws, void *out_f16, void *out_val, uint32_t *out_index, const unsigned long long **total_dev, cudaStream_t st);
@@ -560,6 +561,18 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
     return ws_release(ctx, st);
+}
+
+int pb_stack_from_hwn(pb_ctx *ctx, const void *stack_hwn, int dtype, int N, int H, int W, void *stack_nhw, void *stream) {
+    if (!ctx || !stack_hwn || !stack_nhw || N < 1 || H < 1 || W < 1) return fail(ctx, PB_ERR_ARG, "pb_stack_from_hwn: bad argument");
+    if (stack_hwn == stack_nhw) return fail(ctx, PB_ERR_ARG, "pb_stack_from_hwn: in-place conversion is not supported");
+    if (N > 128) return fail(ctx, PB_ERR_UNSUPPORTED, "pb_stack_from_hwn: more than 128 angles");
+    static const int bytes[4] = {1, 2, 4, 8};
+    if (dtype < 0 || dtype > 3) return fail(ctx, PB_ERR_ARG, "pb_stack_from_hwn: bad dtype");
+    CK(cudaSetDevice(ctx->device));
+    CK(pb_launch_hwn_to_nhw(stack_hwn, stack_nhw, bytes[dtype], (long long)H * W, N, (cudaStream_t)stream));
+    ctx->launches++;
+    return PB_OK;
 }
 
 int pb_rescale_stack(pb_ctx *ctx, const void *values, int dtype, long n, uint16_t *out, double *minmax_host, void *stream) {

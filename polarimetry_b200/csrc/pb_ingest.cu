@@ -1,4 +1,5 @@
-// pb_ingest.cu -- "next" row N3: the numeric part of Polarimetry.define_stack (PyPOLAR.py:1923-1942).
+// pb_ingest.cu -- "next" row N3: the numeric part of Polarimetry.define_stack (PyPOLAR.py:1923-1942), and the
+// layout conversion for angle-minor [H,W,N] stacks.
 //
 // A TIFF stack that is not of an integer type is rescaled to uint16 before anything else sees it (PP:1929-1930):
 //     stack_vals = (65535 * (a - np.amin(a)) / np.ptp(a)).astype(np.uint16)
@@ -68,7 +69,48 @@ __global__ void __launch_bounds__(256) k_rescale(const T *__restrict__ a, long l
     }
 }
 
+// Angle-minor stacks [H,W,N] (pixel-major: the N angles of a pixel are contiguous -- the layout of interleaved acquisitions and
+// the "north-star" variant of SURVEY 8b) -> the reference's angle-major [N,H,W]. One CTA = PPB consecutive pixels: their PPB*N
+// elements are one contiguous span, read with fully coalesced loads into shared memory, then written plane by plane (PPB
+// consecutive elements per plane). Reads and writes the stack once.
+constexpr int PPB = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) k_hwn_to_nhw(const T *__restrict__ in, T *__restrict__ out, long long P, int N) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    T *tile = reinterpret_cast<T *>(tsm);
+    const long long p0 = (long long)blockIdx.x * PPB;
+    const int np = (int)((P - p0) < PPB ? (P - p0) : PPB);
+    const int cnt = np * N;
+    const T *src = in + p0 * N;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) tile[k] = src[k];
+    __syncthreads();
+    for (int k = threadIdx.x; k < N * PPB; k += blockDim.x) {
+        const int n = k / PPB, q = k - n * PPB;
+        if (q < np) out[(long long)n * P + p0 + q] = tile[q * N + n];
+    }
+}
+
 }  // namespace
+
+cudaError_t pb_launch_hwn_to_nhw(const void *in, void *out, int elem_bytes, long long P, int N, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((P + PPB - 1) / PPB);
+    const size_t smem = (size_t)PPB * N * elem_bytes;
+    switch (elem_bytes) {
+    case 1: k_hwn_to_nhw<uint8_t><<<blocks, 256, smem, st>>>((const uint8_t *)in, (uint8_t *)out, P, N); break;
+    case 2: k_hwn_to_nhw<uint16_t><<<blocks, 256, smem, st>>>((const uint16_t *)in, (uint16_t *)out, P, N); break;
+    case 4: k_hwn_to_nhw<float><<<blocks, 256, smem, st>>>((const float *)in, (float *)out, P, N); break;
+    case 8: {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k_hwn_to_nhw<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k_hwn_to_nhw<double><<<blocks, 256, smem, st>>>((const double *)in, (double *)out, P, N);
+        break;
+    }
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
 
 // mm_dev: 3 x unsigned long long workspace. Enqueues the min/max pass and the rescale; *mm_dev keeps (min, max, #NaN) for the caller.
 cudaError_t pb_launch_rescale(const void *a, int is_f64, long long n, unsigned long long *mm_dev, uint16_t *out, cudaStream_t st) {

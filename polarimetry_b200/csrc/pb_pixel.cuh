@@ -201,20 +201,6 @@ __device__ __forceinline__ HarmPix harm_stage_a_core(const PixArgs &a, uint32_t 
     return h;
 }
 
-// threshold / ROI test + stage A (the form the row-march kernel and the one-pixel-per-thread paths use)
-template <int NH>
-__device__ __forceinline__ HarmPix harm_stage_a(const PixArgs &a, long long p, double S0, double Sc, double Ss, double Sc4, double Ss4,
-                                                double Sff, double I) {
-    uint32_t bits;
-    if (!harm_threshold(a, p, I, bits)) {
-        HarmPix h;
-        h.a0 = pb_nan(); h.a2r = h.a2i = h.a4r = h.a4i = 0.0;
-        h.need = false; h.m = false; h.bits = bits;
-        return h;
-    }
-    return harm_stage_a_core<NH>(a, bits, S0, Sc, Ss, Sc4, Ss4, Sff);
-}
-
 // Stage B (PP:3017-3040 outputs, PP:3052, histograms) for a pixel whose fit/chi2 decision is h.m.
 template <int NH>
 __device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem &hs, bool do_hist, const HarmPix &h) {

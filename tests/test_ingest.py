@@ -66,3 +66,32 @@ def test_device_rescale_large_and_float64():
     with pytest.raises(ValueError):
         eng.define_stack(np.ones((8, 8), dtype=np.float32))
     eng.close()
+
+
+@pytest.mark.gpu
+def test_hwn_layout_conversion():
+    """angle-minor [H,W,N] stacks are converted to the reference's [N,H,W] on the device (bit copy), ragged sizes, every
+    dtype, batches; the analysis of the converted stack is the analysis of the original."""
+    import torch
+    from polarimetry_b200 import AnalysisParams, Calibration, Engine, synth
+    eng = Engine(0)
+    rng = np.random.default_rng(9)
+    for dt, N, H, W in ((np.uint16, 18, 37, 53), (np.uint8, 12, 64, 64), (np.float32, 36, 19, 130), (np.float64, 128, 9, 21), (np.uint16, 4, 1, 1)):
+        a = (rng.random((2, H, W, N)) * 250).astype(dt)
+        got = eng.from_hwn(a)
+        assert tuple(got.shape) == (2, N, H, W)
+        g = got.cpu()
+        g = g.view(torch.int16).numpy().view(np.uint16) if dt == np.uint16 else g.numpy()
+        assert np.array_equal(g, np.ascontiguousarray(np.moveaxis(a, -1, 1)))
+    with pytest.raises(RuntimeError):
+        eng.from_hwn(np.zeros((4, 4, 129), dtype=np.uint16))
+    v = synth.stack_1pf(72, 96, 18, seed=77)
+    d = util.load_disk(util.cases.DISK_NODIST)
+    cal = Calibration(d.rho_table, d.psi_table, 401)
+    p = AnalysisParams(method='1PF', dark=480.0, bins=(3, 3), ilow=40000.0)
+    r1 = eng.analyze(v, p, cal)
+    r2 = eng.analyze(eng.from_hwn(np.ascontiguousarray(np.moveaxis(v, 0, -1))), p, cal)
+    for x, y in zip(r1.vars, r2.vars):
+        assert util.eq(x.values.cpu().numpy(), y.values.cpu().numpy())
+    assert util.eq(r1.mask.cpu().numpy(), r2.mask.cpu().numpy())
+    eng.close()
