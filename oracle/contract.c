@@ -356,3 +356,64 @@ long pc_check_markstein_div(double h, long count, uint64_t seed) {
     }
     return bad;
 }
+
+/* ---- the arithmetic of the rows either side of the path ----------------------------------------------- */
+/* define_stack's rescale of a non-integer stack (PyPOLAR.py:1929-1930), one separately rounded operation at a time in the
+ * array's precision: d = a - amin ; m = 65535 * d ; q = m / ptp ; truncation to uint16. */
+void pc_rescale_f32(const float *a, long n, uint16_t *out) {
+    float mn = a[0], mx = a[0];
+    for (long k = 1; k < n; ++k) { if (a[k] < mn) mn = a[k]; if (a[k] > mx) mx = a[k]; }
+    const volatile float ptp = mx - mn;
+    for (long k = 0; k < n; ++k) {
+        volatile float d = a[k] - mn;
+        volatile float m = 65535.0f * d;
+        volatile float q = m / ptp;
+        out[k] = (uint16_t)(q >= 65535.0f ? 65535u : (q > 0.0f ? (unsigned)q : 0u));
+    }
+}
+void pc_rescale_f64(const double *a, long n, uint16_t *out) {
+    double mn = a[0], mx = a[0];
+    for (long k = 1; k < n; ++k) { if (a[k] < mn) mn = a[k]; if (a[k] > mx) mx = a[k]; }
+    const volatile double ptp = mx - mn;
+    for (long k = 0; k < n; ++k) {
+        volatile double d = a[k] - mn;
+        volatile double m = 65535.0 * d;
+        volatile double q = m / ptp;
+        out[k] = (uint16_t)(q >= 65535.0 ? 65535u : (q > 0.0 ? (unsigned)q : 0u));
+    }
+}
+
+/* IEEE binary64 -> binary16, ONE rounding to nearest even (what numpy's astype(np.float16) does, PP:2839, and what the
+ * device's cvt.rn.f16.f64 does): bit pattern of the half. */
+uint16_t pc_f64_to_f16(double x) {
+    uint64_t u; memcpy(&u, &x, 8);
+    const uint16_t sign = (uint16_t)((u >> 48) & 0x8000u);
+    const int e = (int)((u >> 52) & 0x7ff);
+    const uint64_t man = u & 0xfffffffffffffull;
+    if (e == 0x7ff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0u));             /* inf / NaN */
+    if (e == 0) return sign;                                                              /* zero and binary64 subnormals -> 0 */
+    const int eh = e - 1023 + 15;                                                         /* biased half exponent */
+    if (eh >= 31) return (uint16_t)(sign | 0x7c00u);                                      /* overflow -> inf */
+    uint64_t sig = man | (1ull << 52);                                                    /* 53-bit significand */
+    int shift = 42;                                                                       /* 52 - 10 */
+    uint16_t hexp = (uint16_t)eh;
+    if (eh <= 0) {                                                                        /* half subnormal (or underflow) */
+        shift += 1 - eh;
+        hexp = 0;
+        if (shift > 63) return sign;
+    }
+    const uint64_t q = sig >> shift, rem = sig & ((1ull << shift) - 1), half = 1ull << (shift - 1);
+    uint64_t r = q + ((rem > half || (rem == half && (q & 1))) ? 1 : 0);
+    /* normal: q has the implicit bit at position 10; adding the exponent field handles the carry into the next binade */
+    uint32_t h = (eh > 0) ? (uint32_t)(((uint32_t)(hexp - 1) << 10) + (uint32_t)r) : (uint32_t)r;
+    if (h >= 0x7c00u) h = 0x7c00u;
+    return (uint16_t)(sign | h);
+}
+
+/* save_mat's gather (PP:2838-2840): values[sel & isfinite(values)] in row-major order, cast to float16. Returns the count. */
+long pc_compact_f16(const double *v, const uint8_t *sel, long n, uint16_t *out) {
+    long c = 0;
+    for (long k = 0; k < n; ++k)
+        if ((!sel || sel[k]) && finite_d(v[k])) out[c++] = pc_f64_to_f16(v[k]);
+    return c;
+}

@@ -158,3 +158,34 @@ def analyze_stack(values, p: rs.Params, calib=None, rois: Optional[Sequence[dict
                 vmin, vmax = p.ranges[name]
                 res['hist'][(name, s)] = histo(v, sel, name, vmin, vmax, float(p.rotation[1]), p.nbins)
     return res
+
+
+# ---- SURVEY 8f N3 / N4 ------------------------------------------------------------------------------------------
+def rescale(a: np.ndarray) -> np.ndarray:
+    """define_stack's rescale (PP:1929-1930) through the C contract (float32 or float64 stacks)."""
+    a = np.ascontiguousarray(a)
+    out = np.empty(a.shape, dtype=np.uint16)
+    fn = lib().pc_rescale_f32 if a.dtype == np.float32 else lib().pc_rescale_f64
+    if a.dtype not in (np.float32, np.float64):
+        raise TypeError(a.dtype)
+    fn(_p(a), _l(a.size), _p(out))
+    return out
+
+
+def f64_to_f16(x: np.ndarray) -> np.ndarray:
+    """binary64 -> binary16 with one rounding to nearest even, element by element (C contract)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    f = lib().pc_f64_to_f16
+    f.restype, f.argtypes = C.c_uint16, [C.c_double]
+    return np.array([f(float(v)) for v in x], dtype=np.uint16).view(np.float16)
+
+
+def compact_f16(values: np.ndarray, sel: Optional[np.ndarray] = None) -> np.ndarray:
+    """save_mat's gather + cast (PP:2838-2840) through the C contract."""
+    v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    s = None if sel is None else np.ascontiguousarray(sel, dtype=np.uint8).ravel()
+    out = np.empty(v.size, dtype=np.uint16)
+    f = lib().pc_compact_f16
+    f.restype = C.c_long
+    n = f(_p(v), _p(s), _l(v.size), _p(out))
+    return out[:n].view(np.float16)

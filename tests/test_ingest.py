@@ -95,3 +95,13 @@ def test_hwn_layout_conversion():
         assert util.eq(x.values.cpu().numpy(), y.values.cpu().numpy())
     assert util.eq(r1.mask.cpu().numpy(), r2.mask.cpu().numpy())
     eng.close()
+
+
+def test_c_contract_rescale_matches_reference():
+    """oracle/contract.c restates the rescale one rounded operation at a time: identical to what the reference returned."""
+    from oracle import contract
+    g = golden()
+    for kind in ('f32', 'f32_small', 'f32_flatmax'):
+        assert np.array_equal(contract.rescale(g[f'{kind}__in']), g[f'{kind}__out'])
+    a = g['f32__in'].astype(np.float64) * 1.000001
+    assert np.array_equal(contract.rescale(a), rs.define_stack_values(a))

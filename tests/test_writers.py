@@ -103,3 +103,23 @@ def test_compact_properties_large():
     assert eng.compact(z)['count'] == 0
     assert eng.compact(torch.zeros(5000, device='cuda', dtype=torch.float64))['count'] == 5000
     eng.close()
+
+
+def test_c_contract_half_rounding_and_gather():
+    """binary64 -> binary16 in ONE rounding (numpy's astype, the device's cvt.rn.f16.f64): the C contract against numpy on
+    ties, subnormals, overflow, NaN and random values; and the gather against the reference's .mat arrays."""
+    from oracle import contract
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-200, 200, 4000), rng.uniform(-1e-6, 1e-6, 500), 10.0 ** rng.uniform(-9, 6, 500),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, 65504.0, 65519.99, 65520.0, 1e9, 5.96e-8, 2.98e-8, 2.9802322387695312e-08,
+                         6.1e-5, 6.097555160522461e-05, 1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11, 2049.0, 2051.0, 179.96875, 179.984375]])
+    with np.errstate(over='ignore'):
+        ref = x.astype(np.float16)
+    got = contract.f64_to_f16(x)
+    assert np.array_equal(got.view(np.uint16)[~np.isnan(x)], ref.view(np.uint16)[~np.isnan(x)])
+    assert np.isnan(got[np.isnan(x)]).all()
+    g = golden()
+    p = rs.Params(method='1PF', dark=CASE['dark'], bins=CASE['bins'], ilow=CASE['ilow'], rotation=CASE['rotation'])
+    res = rs.analyze_stack(g['values'], p, util.load_disk(util.cases.DISK_NODIST), None, False, for_calib=False)
+    for k in ('Rho', 'Psi'):
+        assert np.array_equal(contract.compact_f16(res['vars'][k]).astype(np.float64), g[f'whole__mat_{k}'])
