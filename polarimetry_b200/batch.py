@@ -61,3 +61,34 @@ class BatchAnalyzer:
         if reduce:
             allreduce_sum_(o['hist'], self.group)
         return o
+
+
+def place_frames(hist_local: torch.Tensor, own: range, n_frames: int) -> torch.Tensor:
+    """Per-frame results of this rank's frames `own` in a [n_frames, ...] buffer that is zero for the frames of the other ranks:
+    the SUM all-reduce of these buffers is the whole series."""
+    if hist_local.shape[0] != len(own):
+        raise ValueError(f'{hist_local.shape[0]} local frames for a shard of {len(own)}')
+    full = torch.zeros((n_frames,) + tuple(hist_local.shape[1:]), dtype=hist_local.dtype, device=hist_local.device)
+    if len(own):
+        full[own.start:own.stop] = hist_local
+    return full
+
+
+class TimeSeriesAnalyzer:
+    """Time-series mode (BASELINE configs[4]): the frames of a series are sharded over the ranks (shard_range); every frame keeps its
+    own histograms; one all-reduce of the [n_frames, groups, vars, nbins] buffer gives every rank the whole series."""
+
+    def __init__(self, engine, params, calib=None, rois: Optional[Sequence[dict]] = None, per_roi: bool = False, group=None):
+        self.engine, self.params, self.calib, self.rois, self.per_roi, self.group = engine, params, calib, rois, per_roi, group
+
+    def run(self, frames_local, n_frames: int, rank: int, world: int, reduce: bool = True) -> dict:
+        """frames_local: this rank's frames [len(shard_range(n_frames, rank, world)), N, H, W] (device tensor). Returns the engine's
+        output dict (maps of the local frames) with o['hist_frames']: int64 [n_frames, n_groups, n_vars, nbins]."""
+        own = shard_range(n_frames, rank, world)
+        o = self.engine.analyze_batch(frames_local, self.params, self.calib, self.rois, self.per_roi, want_intensity=False,
+                                      hist_per_stack=True)
+        full = place_frames(o['hist'], own, n_frames)
+        if reduce:
+            allreduce_sum_(full, self.group)
+        o['hist_frames'] = full
+        return o

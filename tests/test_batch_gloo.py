@@ -67,3 +67,43 @@ def test_two_rank_histogram_allreduce_matches_merged_histogram():
     fin = allv[np.isfinite(allv)]
     assert int(mom[0]) == fin.size
     assert abs(batch.circular_mean_from_moments(torch.from_numpy(mom)) - rs.circularmean(fin)) < 1e-9
+
+
+def _frame_hist(k):
+    rng = np.random.default_rng(900 + k)
+    return torch.from_numpy(rng.integers(0, 1000, size=(2, 3, 16), dtype=np.int64))
+
+
+def _ts_worker(rank, world, port, n_frames, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    own = batch.shard_range(n_frames, rank, world)
+    local = torch.stack([_frame_hist(k) for k in own]) if len(own) else torch.zeros((0, 2, 3, 16), dtype=torch.int64)
+    full = batch.place_frames(local, own, n_frames)
+    batch.allreduce_sum_(full)
+    q.put((rank, full.numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n_frames', [5, 1])
+def test_two_rank_time_series_frames(n_frames):
+    """configs[4] semantics on CPU (gloo, world 2): per-frame histograms placed in a zero buffer and all-reduced once give every rank
+    the whole series, also when a rank owns no frame."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_ts_worker, args=(r, world, port, n_frames, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get() for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = np.stack([_frame_hist(k).numpy() for k in range(n_frames)])
+    for r in range(world):
+        assert np.array_equal(got[r], want)
+    with pytest.raises(ValueError):
+        batch.place_frames(torch.zeros((2, 4)), range(0, 3), 5)

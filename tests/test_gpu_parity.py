@@ -421,3 +421,21 @@ def test_time_series_per_frame_histograms(eng):
         for k in range(4):
             ref = rs.analyze_stack(frames[k], rs.Params(method='1PF', dark=480.0, bins=bins, ilow=38000.0), ocal)
             assert util.eq(per[k, 0, 0], ref['hist'][('Rho', None)]) and util.eq(per[k, 0, 1], ref['hist'][('Psi', None)])
+
+
+def test_time_series_analyzer_places_frames(eng):
+    """TimeSeriesAnalyzer (configs[4]): a rank that owns frames [2, 4) of a 6-frame series returns a [6, ...] buffer holding
+    its two frames' histograms (equal to the per-frame analysis) and zeros elsewhere."""
+    from polarimetry_b200 import synth
+    from polarimetry_b200.batch import TimeSeriesAnalyzer, shard_range
+    frames = np.stack([synth.stack_1pf(40, 72, 18, seed=320 + k) for k in range(6)])
+    cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
+    p = AnalysisParams(method='1PF', dark=480.0, bins=(3, 3), ilow=38000.0)
+    own = shard_range(6, 1, 3)
+    assert (own.start, own.stop) == (2, 4)
+    o = TimeSeriesAnalyzer(eng, p, cal).run(eng._to_device(frames[own.start:own.stop]), 6, 1, 3, reduce=False)
+    hf = o['hist_frames'].cpu().numpy()
+    assert hf.shape == (6, 1, 2, 60)
+    assert not hf[:2].any() and not hf[4:].any()
+    ref = eng.analyze_batch(frames, p, cal, hist_per_stack=True)['hist'].cpu().numpy()
+    assert util.eq(hf[2:4], ref[2:4])
