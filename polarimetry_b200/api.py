@@ -731,6 +731,11 @@ class Engine:
         yy = torch.arange(H, device=m.device, dtype=torch.int32)[:, None].expand(H, W)
         zero = torch.zeros((), dtype=torch.int32, device=m.device)
         d = {'X': torch.where(m, xx, zero).cpu().numpy().astype(np.uint16), 'Y': torch.where(m, yy, zero).cpu().numpy().astype(np.uint16)}
+        ct = res.get_var('Rho_contour')
+        if ct is not None:                               # PP:2835-2836: xct / yct are NaN outside isfinite(Rho_contour) (PP:3063)
+            mc = torch.isfinite(ct.values)
+            d.update({'X_contour': torch.where(mc, xx, zero).cpu().numpy().astype(np.uint16),
+                      'Y_contour': torch.where(mc, yy, zero).cpu().numpy().astype(np.uint16)})
         gb = self._group_bits(res, roi_index, group)
         for var in res.vars:
             d[var.name] = self.compact(var.values, None, None, res.roi_map, gb, want=('f16',))['f16'].cpu().numpy()
@@ -756,6 +761,24 @@ class Engine:
             cols.append(col.cpu().numpy())
         return names, cols
 
+    def csv_contour_columns(self, res: Result, roi_index: Optional[int] = None, group: int = 0) -> Tuple[List[str], List[np.ndarray]]:
+        """The contour table of save_csv (PP:2803-2810, PP:2819-2826): X_ct, Y_ct and every *_contour variable under
+        `roi & isfinite(Rho_contour)`."""
+        ct = res.get_var('Rho_contour')
+        if ct is None:
+            raise ValueError('csv_contour_columns: the analysis had no edge contours')
+        W = res.mask.shape[-1]
+        gb = self._group_bits(res, roi_index, group)
+        first = self.compact(ct.values, None, None, res.roi_map, gb, want=('val', 'index'))
+        idx = first['index'].cpu().numpy().astype(np.int64)
+        names, cols = ['X_ct', 'Y_ct'], [(idx % W).astype(np.uint16), (idx // W).astype(np.int16)]
+        for var in res.vars:
+            if '_contour' in var.name:
+                col = first['val'] if var is ct else self.compact(var.values, ct.values, None, res.roi_map, gb, want=('val',))['val']
+                names.append(var.name)
+                cols.append(col.cpu().numpy())
+        return names, cols
+
     def save_mat(self, res: Result, path, method: str, source: str = '', roi_index: Optional[int] = None, group: int = 0) -> None:
         """save_mat (PP:2829-2842) on device-resident results."""
         from datetime import date
@@ -768,13 +791,17 @@ class Engine:
         """save_csv (PP:2794-2818, non-contour table) on device-resident results; floats as '%.3f' (PP:2791-2792)."""
         import csv
         from datetime import date
-        names, cols = self.csv_columns(res, roi_index, group)
-        fmt = [[f'{x:.3f}' if isinstance(x, float) else x for x in (c.tolist() if c.dtype.kind == 'f' else list(c))] for c in cols]
-        with open(path, 'w', newline='') as f:
-            w = csv.writer(f, delimiter=',', quoting=csv.QUOTE_MINIMAL)
-            w.writerow([f"{method}, file: {source}, date: {date.today().strftime('%B %d %Y')}"])
-            w.writerow(names)
-            w.writerows(zip(*fmt))
+        tables = [(Path(path), self.csv_columns(res, roi_index, group))]
+        if res.get_var('Rho_contour') is not None:       # second file '<stem>_contour.csv' (PP:2819-2826)
+            pth = Path(path)
+            tables.append((pth.with_name(pth.stem + '_contour' + pth.suffix), self.csv_contour_columns(res, roi_index, group)))
+        for pth, (names, cols) in tables:
+            fmt = [[f'{x:.3f}' if isinstance(x, float) else x for x in (c.tolist() if c.dtype.kind == 'f' else list(c))] for c in cols]
+            with open(pth, 'w', newline='') as f:
+                w = csv.writer(f, delimiter=',', quoting=csv.QUOTE_MINIMAL)
+                w.writerow([f"{method}, file: {source}, date: {date.today().strftime('%B %d %Y')}"])
+                w.writerow(names)
+                w.writerows(zip(*fmt))
 
     def launch_count(self) -> int:
         return int(self.lib.pb_launch_count(self._ctx))

@@ -12,7 +12,17 @@ from tests import util
 CASE = dict(dark=480.0, ilow=38000.0, bins=(3, 3), rotation=(17.0, 5.0, 0.0))
 ROIS = [dict(indx=1, select=True, ILow=30000.0, vertices=np.array([[5.2, 90.7, 90.1, 6.0], [4.0, 6.5, 70.2, 60.9]])),
         dict(indx=3, select=True, ILow=42000.0, vertices=np.array([[40.0, 110.0, 75.5], [10.0, 40.0, 78.0]]))]
-VARIANTS = (('whole', None, False, None, 0), ('roi3', ROIS, True, 3, 1), ('union', ROIS, False, None, 0))
+VARIANTS = (('whole', None, False, None, 0), ('roi3', ROIS, True, 3, 1), ('union', ROIS, False, None, 0),
+            ('contour', None, False, None, 0), ('contour_roi1', ROIS, True, 1, 0))
+
+
+def edge_for(tag, shape):
+    from oracle import cases
+    return cases.make_edge(shape) if tag.startswith('contour') else None
+
+
+def mat_keys(tag):
+    return ('X', 'Y', 'Rho', 'Psi') + (('X_contour', 'Y_contour', 'Rho_contour', 'Psi_contour') if tag.startswith('contour') else ())
 
 
 def golden():
@@ -28,14 +38,19 @@ def table(cols):
 def test_oracle_writers_match_reference_files(tag, rois, per_roi, roi, group):
     g = golden()
     p = rs.Params(method='1PF', dark=CASE['dark'], bins=CASE['bins'], ilow=CASE['ilow'], rotation=CASE['rotation'])
-    res = rs.analyze_stack(g['values'], p, util.load_disk(util.cases.DISK_NODIST), rois, per_roi, for_calib=False)
+    res = rs.analyze_stack(g['values'], p, util.load_disk(util.cases.DISK_NODIST), rois, per_roi, edge_contours=edge_for(tag, g['values'].shape[1:]),
+                           for_calib=False)
     m = rs.mat_arrays(res, res['roi_map'], roi)
-    for k in ('X', 'Y', 'Rho', 'Psi'):
+    for k in mat_keys(tag):
         assert np.array_equal(g[f'{tag}__mat_{k}'].astype(np.float64), m[k].astype(np.float64)), (tag, k)
     assert m['Rho'].dtype == np.float16
     names, cols = rs.csv_columns(res, res['roi_map'], roi)
     assert list(names) == list(g[f'{tag}__csv_names'])
     assert np.array_equal(table(cols), g[f'{tag}__csv_rows'])
+    if tag.startswith('contour'):
+        names, cols = rs.csv_contour_columns(res, res['roi_map'], roi)
+        assert list(names) == list(g[f'{tag}__csvct_names'])
+        assert np.array_equal(table(cols), g[f'{tag}__csvct_rows'])
 
 
 @pytest.mark.gpu
@@ -47,14 +62,18 @@ def test_device_writers_match_reference_files(tag, rois, per_roi, roi, group, tm
     d = util.load_disk(util.cases.DISK_NODIST)
     eng = Engine(0)
     p = AnalysisParams(method='1PF', dark=CASE['dark'], bins=CASE['bins'], ilow=CASE['ilow'], rotation=CASE['rotation'])
-    res = eng.analyze(g['values'], p, Calibration(d.rho_table, d.psi_table, 401), rois, per_roi)
+    res = eng.analyze(g['values'], p, Calibration(d.rho_table, d.psi_table, 401), rois, per_roi, None, edge_for(tag, g['values'].shape[1:]))
     m = eng.mat_arrays(res, roi, group)
-    for k in ('X', 'Y', 'Rho', 'Psi'):
-        assert m[k].dtype == (np.uint16 if k in 'XY' else np.float16)
+    for k in mat_keys(tag):
+        assert m[k].dtype == (np.uint16 if k[0] in 'XY' else np.float16)
         assert np.array_equal(g[f'{tag}__mat_{k}'].astype(np.float64), m[k].astype(np.float64)), (tag, k)
     names, cols = eng.csv_columns(res, roi, group)
     assert list(names) == list(g[f'{tag}__csv_names'])
     assert np.array_equal(table(cols), g[f'{tag}__csv_rows'])
+    if tag.startswith('contour'):
+        names, cols = eng.csv_contour_columns(res, roi, group)
+        assert list(names) == list(g[f'{tag}__csvct_names'])
+        assert np.array_equal(table(cols), g[f'{tag}__csvct_rows'])
     # and the files themselves
     eng.save_mat(res, tmp_path / 'o.mat', '1PF', 'synthetic.tif', roi, group)
     eng.save_csv(res, tmp_path / 'o.csv', '1PF', 'synthetic.tif', roi, group)
@@ -66,6 +85,11 @@ def test_device_writers_match_reference_files(tag, rois, per_roi, roi, group, tm
         rows = list(csv.reader(f))
     assert rows[1] == list(g[f'{tag}__csv_names'])
     assert np.array_equal(np.array(rows[2:], dtype=str).reshape(-1, 4), g[f'{tag}__csv_rows'])
+    if tag.startswith('contour'):
+        with open(tmp_path / 'o_contour.csv', newline='') as f:
+            rows = list(csv.reader(f))
+        assert rows[1] == list(g[f'{tag}__csvct_names'])
+        assert np.array_equal(np.array(rows[2:], dtype=str).reshape(-1, 4), g[f'{tag}__csvct_rows'])
     eng.close()
 
 
