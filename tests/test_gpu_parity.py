@@ -439,3 +439,20 @@ def test_time_series_analyzer_places_frames(eng):
     assert not hf[:2].any() and not hf[4:].any()
     ref = eng.analyze_batch(frames, p, cal, hist_per_stack=True)['hist'].cpu().numpy()
     assert util.eq(hf[2:4], ref[2:4])
+
+
+def test_full_size_time_series_frame_properties():
+    """BASELINE configs[4] at its FULL frame size (8192x8192x90 uint16, 12.1 GB, bin 5x5) -- the oracle cannot run this size, so the
+    checks are size-independent properties: rows of the full-frame maps are bit-identical to the analysis of full-width row crops
+    at the top edge, beyond the 2^32-element offset and at the bottom edge; the rho histogram total equals the valid-pixel count."""
+    import importlib.util
+    from pathlib import Path
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip('needs 40 GB of free device memory')
+    spec = importlib.util.spec_from_file_location('c5_frame', Path(__file__).resolve().parent.parent / 'tools' / 'c5_frame.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.run(8192, 90, 5, reps=1)
+    assert r['plan'] == 'fused_march' and r['all_ok'], r['checks']
+    assert 0.2 < r['valid_pixel_fraction'] < 0.6
