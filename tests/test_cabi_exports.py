@@ -54,3 +54,18 @@ def test_product_never_imports_the_oracle():
         assert 'oracle' not in src, f
     for f in (ROOT / 'polarimetry_b200' / 'csrc').iterdir():
         assert 'oracle/' not in f.read_text().replace('oracle/contract.c', ''), f
+
+
+def test_flag_constants_match_header():
+    """The ctypes mirror carries the header's flag / enum values (a drifted constant would silently select another code path)."""
+    from polarimetry_b200 import _cabi
+    h = (ROOT / 'include' / 'polar_b200.h').read_text()
+    flags = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(PB_FLAG_[A-Z0-9_]+)\s+(\d+)u', h)}
+    assert flags == {'PB_FLAG_OUT_F64': _cabi.FLAG_OUT_F64, 'PB_FLAG_NO_HIST': _cabi.FLAG_NO_HIST, 'PB_FLAG_EXACT_CHI2': _cabi.FLAG_EXACT_CHI2,
+                     'PB_FLAG_FORCE_UNFUSED': _cabi.FLAG_FORCE_UNFUSED, 'PB_FLAG_PROJECT_ONLY': _cabi.FLAG_PROJECT_ONLY}
+    m = re.search(r'typedef enum pb_dtype \{([^}]*)\}', h)
+    dt = {k.strip(): int(v) for k, v in (x.split('=') for x in m.group(1).split(','))}
+    assert dt == {'PB_U8': _cabi.DTYPES['uint8'], 'PB_U16': _cabi.DTYPES['uint16'], 'PB_F32': _cabi.DTYPES['float32'], 'PB_F64': _cabi.DTYPES['float64']}
+    for name, val in (('PB_MAX_ROIS', _cabi.PB_MAX_ROIS), ('PB_MAX_VARS', _cabi.PB_MAX_VARS), ('PB_MAX_BINS', _cabi.PB_MAX_BINS)):
+        mm = re.search(r'#define\s+' + name + r'\s+(\d+)', h)
+        assert mm and int(mm.group(1)) == val, name
