@@ -823,6 +823,11 @@ def get_intensity(self, dark: float = 0.0, bin: List[int] = [1, 1]) -> np.ndarra
     return default_engine().get_intensity(self.values, dark, [int(b) for b in bin]).cpu().numpy()
 
 
+def compute_dark(self, size_cell: int = 20) -> float:
+    """Drop-in for Stack.compute_dark (PC:266-278); `self` is a reference Stack (integer stacks, as read from the TIFF)."""
+    return default_engine().compute_dark(self.values, int(size_cell))
+
+
 def binning(self, field: np.ndarray) -> np.ndarray:
     """Drop-in for Polarimetry.binning (PP:2942-2946); `self` is the reference application object."""
     bins = [int(sb.get()) for sb in self.bin_spinboxes]
@@ -880,3 +885,4 @@ def install(pypolar_module, classes_module=None) -> None:
     stack_cls = getattr(classes_module, 'Stack', None) or getattr(pypolar_module, 'Stack', None)
     if stack_cls is not None:
         stack_cls.get_intensity = get_intensity
+        stack_cls.compute_dark = compute_dark

@@ -380,6 +380,7 @@ def test_drop_in_functions_with_reference_signatures(eng):
     stack = types.SimpleNamespace(values=v)
     intensity = pb.get_intensity(stack, dark=c['dark'], bin=[c['bins'][0], c['bins'][1]])
     assert util.eq(intensity, g['intensity'])
+    assert pb.compute_dark(stack) == rs.compute_dark(v) and pb.compute_dark(stack, 16) == rs.compute_dark(v, 16)   # PC:266-278
     field = np.maximum(v - (c['dark'] + 0.0), 0)
     field = pb.binning(app, field)
     assert util.eq(field, rs.binning(rs.preprocess(v, p), p.bins))
