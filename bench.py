@@ -28,11 +28,31 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-H, W, N = 2048, 2048, 18
+H = int(os.environ.get('PB_BENCH_H', '2048'))          # development knob only: the driver runs the 2048 x 2048 default
+W = int(os.environ.get('PB_BENCH_W', str(H)))
+N = 18
 WORKLOADS = {'1pf': ('1PF', 18), 'shg': ('SHG', 36), '4polar3d': ('4POLAR 3D', 4), '1pf90': ('1PF', 90)}   # BASELINE configs[3] (headline), [1], [2]
 DISK = ROOT / 'tests' / 'golden' / 'calib' / 'Disk_Ga0_Pa0_Ta0_Gb0_Pb0_Tb0_Gc0_Pc0_Tc0.npz'
-DARK, ILOW = 480.0, 40000.0
+DARK = 480.0
+ILOW_PERCENTILE = 20.0        # SURVEY 8d generator G1: threshold at the 20th percentile of the total-intensity image ('{:.0f}'-rounded)
 OUT_BYTES_PER_PIXEL = 13      # rho f32 + psi f32 + intmap f32 + mask u8
+
+
+def g1_ilow(intensity: np.ndarray) -> float:
+    """ILow = 20th percentile of the intensity image, rounded as the reference GUI formats it (PP:644, PP:2148)."""
+    return float('{:.0f}'.format(np.percentile(np.asarray(intensity, dtype=np.float64), ILOW_PERCENTILE)))
+
+
+def digest(res_maps):
+    """Order-independent-free fingerprint of one stack's results: (valid pixels, crc of the mask, crc of each f32 map with NaN -> -1)."""
+    import zlib
+    out = []
+    for m in res_maps:
+        a = np.ascontiguousarray(m)
+        if a.dtype.kind == 'f':
+            a = np.nan_to_num(a.astype(np.float32), nan=-1.0)
+        out.append(zlib.crc32(a.tobytes()))
+    return out
 
 
 def measured_peak_gbs():
@@ -79,82 +99,124 @@ class ClockSampler:
 
 
 # ---- CPU side: the oracle restatement (== the reference's NumPy/SciPy statements) ---------------------------
-_CPU_STACKS = {}
+# Only this leg (cpu_baseline / --impl reference) may execute oracle/. One worker process per host core, capped by RAM
+# (2.8 GB peak RSS per 2048x2048x18 stack); the pool stays alive across steps; the timed work per stack is
+# what the GPU arm's step produces: threshold image, maps, mask and the rho/psi histograms (no statistics rows).
+_CPU = {}
 
 
 def _cpu_prepare(args):
     """Worker side, untimed: generate this worker's stacks and load the calibration table."""
-    seeds, h, w = args
+    seeds, h, w, n = args
     from oracle import restate as rs
     from polarimetry_b200 import synth
     d = np.load(DISK)
-    _CPU_STACKS['cal'] = rs.Calib.from_disk(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-    _CPU_STACKS['stacks'] = [synth.stack_1pf(h, w, 18, seed=s) for s in seeds]
-    rs.analyze_stack(synth.stack_1pf(64, 64, 18, seed=0), rs.Params(method='1PF', dark=DARK, bins=(3, 3), ilow=ILOW), _CPU_STACKS['cal'])
+    _CPU['cal'] = rs.Calib.from_disk(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
+    _CPU['stacks'] = [(sd, synth.stack_1pf(h, w, n, seed=sd)) for sd in seeds]
+    rs.analyze_stack(synth.stack_1pf(64, 64, n, seed=0), rs.Params(method='1PF', dark=DARK, bins=(3, 3), ilow=1000.0), _CPU['cal'], want_stats=False)
     return len(seeds)
 
 
-def _cpu_run(bins):
+def _cpu_run(args):
     """Worker side, timed: the reference's analysis path (oracle/restate.py) on every stack of this worker."""
+    bins, ilow, want_digest = args
     from oracle import restate as rs
-    for v in _CPU_STACKS['stacks']:
-        rs.analyze_stack(v, rs.Params(method='1PF', dark=DARK, bins=bins, ilow=ILOW), _CPU_STACKS['cal'])
-    return len(_CPU_STACKS['stacks'])
+    out = []
+    for sd, v in _CPU['stacks']:
+        r = rs.analyze_stack(v, rs.Params(method='1PF', dark=DARK, bins=bins, ilow=ilow), _CPU['cal'], want_stats=False)
+        rec = {'seed': sd, 'valid': int(r['mask'].sum())}
+        if want_digest:
+            rec['hist'] = [r['hist'][('Rho', None)].tolist(), r['hist'][('Psi', None)].tolist()]
+            rec['crc'] = digest([r['mask'].astype(np.uint8), r['vars']['Rho'], r['vars']['Psi'], r['intmap']])
+        out.append(rec)
+    return out
 
 
-def cpu_sample(bins, workers: int, h: int = 1024, w: int = 1024, per_worker: int = 1):
-    """The oracle on `workers*per_worker` stacks of h x w x 18, one process per host core, stacks pre-generated in the
-    workers (untimed); returns (Mpx-angles/s, seconds) of the analysis alone."""
-    import multiprocessing as mp
-    ctx = mp.get_context('spawn')
-    with ctx.Pool(workers) as pool:
-        jobs = [([1000 + k * per_worker + j for j in range(per_worker)], h, w) for k in range(workers)]
-        pool.map(_cpu_prepare, jobs, chunksize=1)
-        t0 = time.perf_counter()
-        done = sum(pool.map(_cpu_run, [bins] * workers, chunksize=1))
-        dt = time.perf_counter() - t0
-    return done * h * w * 18 / dt / 1e6, dt
-
-
-def host_workers():
+def host_workers(bytes_per_worker: float = 3.2e9):
     n = os.cpu_count() or 1
     try:
         n = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    try:
+        avail = next(int(l.split()[1]) * 1024 for l in open('/proc/meminfo') if l.startswith('MemAvailable'))
+        n = min(n, max(1, int(0.7 * avail / bytes_per_worker)))
+    except Exception:
+        pass
     return max(1, min(n, 32))
+
+
+class CpuArm:
+    """A pool of worker processes holding pre-generated stacks (seeds 0, 1, ... : worker k owns seeds [k*per, (k+1)*per))."""
+
+    def __init__(self, workers: int, per_worker: int, n: int = 18, h: int = H, w: int = W):
+        import multiprocessing as mp
+        self.workers, self.per, self.shape = workers, per_worker, (n, h, w)
+        self.pool = mp.get_context('spawn').Pool(workers)
+        jobs = [([k * per_worker + j for j in range(per_worker)], h, w, n) for k in range(workers)]
+        self.pool.map(_cpu_prepare, jobs, chunksize=1)
+
+    def step(self, bins, ilow, want_digest=False):
+        """One pass over every worker's stacks: (Mpx-angles/s, seconds, per-stack records)."""
+        t0 = time.perf_counter()
+        recs = self.pool.map(_cpu_run, [(bins, ilow, want_digest)] * self.workers, chunksize=1)
+        dt = time.perf_counter() - t0
+        flat = [r for w in recs for r in w]
+        n, h, w = self.shape
+        return len(flat) * h * w * n / dt / 1e6, dt, flat
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_ilow(bins, n: int = 18) -> float:
+    """G1 threshold from the oracle's threshold image of the seed-0 stack (the reference arm must not touch the GPU)."""
+    from oracle import restate as rs
+    from polarimetry_b200 import synth
+    return g1_ilow(rs.get_intensity(synth.stack_1pf(H, W, n, seed=0), DARK, bins))
 
 
 def run_reference_arm(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if a.workload != '1pf':
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU arm times the headline 1pf workload only'}))
+        return
     bins = (a.bin, a.bin)
+    ilow = a.ilow if a.ilow is not None else cpu_ilow(bins)
     workers = host_workers()
-    vals = []
+    arm = CpuArm(workers, 1)
+    vals, valid = [], 0
     for s in range(a.warmup + a.steps):
-        v, dt = cpu_sample(bins, workers, per_worker=1)
+        v, dt, recs = arm.step(bins, ilow)
+        valid = sum(r['valid'] for r in recs) / (len(recs) * H * W)
         if s >= a.warmup:
             vals.append((v, dt))
+    arm.close()
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals]) * 1e3)
-    sample = f'{workers} stacks 1024x1024x18 uint16 per step, one per worker process (oracle/restate.py = the reference\'s NumPy/SciPy statements)'
+    sample = (f'{workers} stacks {H}x{W}x18 uint16 per step, one per worker process, {workers} processes kept alive across steps '
+              f'(oracle/restate.py = the reference\'s NumPy/SciPy statements: threshold image, maps, mask, rho/psi histograms)')
     line = {'impl': 'reference', 'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': a.gpus, 'steps': a.steps,
             'warmup': a.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(a, None),
+            'data': 'synthetic', 'config': workload_config(a, ilow), 'stacks_per_step': workers, 'valid_pixel_fraction': round(valid, 4),
             'cpu_baseline': {'value': value, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
 
 
-def workload_config(a, batch):
+def workload_config(a, ilow):
+    """The workload both arms run -- identical in the two JSON lines (per-run facts such as the resident batch live outside)."""
     wl = getattr(a, 'workload', '1pf')
-    text = {'1pf': f'1PF batch of {H}x{W}x18 uint16 stacks, dark {DARK:.0f}, bin {a.bin}x{a.bin}, disk-cone LUT (no distortion), '
-                   f'threshold, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
+    text = {'1pf': f'1PF batch of {H}x{W}x18 uint16 stacks (BASELINE configs[3] per-GPU share; generator G1), dark {DARK:.0f}, bin {a.bin}x{a.bin}, '
+                   f'disk-cone LUT (no distortion), threshold at the 20th percentile of the intensity image, rho/psi/intensity maps f32 + mask + rho/psi histograms (60 bins)',
             'shg': f'SHG batch of {H}x{W}x36 uint16 stacks (BASELINE configs[1]), bin {a.bin}x{a.bin}, rho/S2/S4/S_SHG/intensity maps f32 + mask + histograms',
             '4polar3d': f'4POLAR 3D batch of 4x{H}x{W} uint16 (BASELINE configs[2]), bin {a.bin}x{a.bin}, rho/psi/eta/intensity maps f32 + mask + histograms',
             '1pf90': f'1PF batch of {H}x{W}x90 uint16 stacks (the per-frame shape of BASELINE configs[4] at 1/16 of its field), bin {a.bin}x{a.bin}, maps f32 + mask + histograms'}[wl]
-    return {'workload': text, 'ilow': getattr(a, 'ilow', ILOW), 'stacks_per_gpu': batch, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
+    return {'workload': text, 'ilow': ilow, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)',
+            'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
 
 
 def main():
@@ -167,7 +229,8 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=16, help='stacks per host-buffer call of the e2e leg (8: 0.90, 16: 0.92, 32: 0.94 of the pinned-H2D ceiling)')
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--ilow', type=float, default=ILOW, help='intensity threshold (1pf workload); 0 keeps every pixel')
+    ap.add_argument('--ilow', type=float, default=None, help='intensity threshold (1pf workloads); default = SURVEY G1 (20th percentile of the '
+                                                             'intensity image, ~80 %% of the pixels valid); 0 keeps every pixel')
     ap.add_argument('--workload', default='1pf', choices=sorted(WORKLOADS), help='1pf = the headline (BASELINE configs[3]); shg / 4polar3d = configs[1] / [2], reported for information')
     a = ap.parse_args()
     if a.impl == 'reference':
@@ -191,15 +254,20 @@ def main():
     d = np.load(DISK)
     if method == '1PF':
         cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=a.ilow * N / 18.0, out_dtype='float32')
         gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed)
+        ilow = a.ilow
+        if ilow is None:      # G1 threshold from the threshold image of the seed-0 stack, through the product's own seam
+            ilow = g1_ilow(eng.get_intensity(gen(0), DARK, (a.bin, a.bin)).cpu().numpy())
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32')
     elif method == 'SHG':
         cal = None
-        p = AnalysisParams(method='SHG', dark=0.0, bins=(a.bin, a.bin), ilow=40000.0, out_dtype='float32')
+        ilow = 40000.0
+        p = AnalysisParams(method='SHG', dark=0.0, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32')
         gen = lambda seed: synth.stack_4harm(H, W, N, seed=seed)
     else:
         cal = Calibration.from_K(synth.K_TH_3D)
-        p = AnalysisParams(method='4POLAR 3D', dark=0.0, bins=(a.bin, a.bin), ilow=1000.0, out_dtype='float32')
+        ilow = 1000.0
+        p = AnalysisParams(method='4POLAR 3D', dark=0.0, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32')
         gen = lambda seed: synth.stack_4polar(H, W, seed=seed, three_d=True)
     out_bpp = {'1PF': 13, 'SHG': 21, '4POLAR 3D': 17}[method]
 
@@ -306,16 +374,41 @@ def main():
            'frac_of_h2d_ceiling': round(e2e_val * 1e6 * 2 / 1e9 / h2d_gbs, 3),
            'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
 
-    cpu = None
+    # size-independent sanity of the timed outputs: every valid pixel has a rho inside [0, 180] -> one histogram count each
+    hist_np = out['hist'].cpu().numpy()
+    n_valid = int(out['mask'].sum().item())
+    assert int(hist_np[0, 0, 0].sum()) == n_valid, (int(hist_np[0, 0, 0].sum()), n_valid)
+
+    cpu = parity = None
     if rank == 0 and world == 1 and not a.no_cpu and a.workload == '1pf':
+        # cpu_baseline leg: the oracle on the GPU box's host cores, on a bounded sample of the same workload (same generator,
+        # seeds 0.., same threshold), and -- the oracle acting as the checker -- the GPU results of the first distinct stacks of
+        # the timed batch compared with it: histograms and mask / map checksums must be identical.
         workers = host_workers()
-        v, dt = cpu_sample((a.bin, a.bin), workers, per_worker=8)
+        arm = CpuArm(workers, 1)
+        arm.step((a.bin, a.bin), ilow)                                   # warm-up pass
+        v, dt, recs = arm.step((a.bin, a.bin), ilow, want_digest=True)
+        arm.close()
         cpu = {'value': v, 'unit': 'Mpx-angles/s', 'cores': workers, 'kind': 'port',
-               'sample': f'{8 * workers} stacks 1024x1024x18 (8 per worker process, {workers} processes) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements)'}
+               'sample': f'{len(recs)} stacks {H}x{W}x18 (one per worker process, {workers} processes) in {dt:.1f} s, oracle/restate.py (the reference\'s NumPy/SciPy statements: threshold image, maps, mask, rho/psi histograms)'}
+        by_seed = {r['seed']: r for r in recs}
+        ncheck = [k for k in range(ndistinct) if k in by_seed]
+        ok = True
+        for k in ncheck:
+            g = digest([out['mask'][k].cpu().numpy(), out['vars']['Rho'][k].cpu().numpy(), out['vars']['Psi'][k].cpu().numpy(), out['intmap'][k].cpu().numpy()])
+            ok = ok and g == by_seed[k]['crc'] and int(out['mask'][k].sum().item()) == by_seed[k]['valid']
+        hist_ok = None
+        if len(ncheck) == ndistinct and B % ndistinct == 0:
+            want = (B // ndistinct) * sum(np.asarray(by_seed[k]['hist'], dtype=np.int64) for k in ncheck)
+            hist_ok = bool(np.array_equal(hist_np[0, 0], want))
+            ok = ok and hist_ok
+        parity = {'checked_stacks': len(ncheck), 'maps_mask_crc_equal': bool(ok), 'batch_histograms_equal': hist_ok}
+        assert ok, f'GPU results differ from the oracle: {parity}'
     if rank == 0:
         line = {'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-                'data': 'synthetic', 'config': dict(workload_config(a, B), valid_pixel_fraction=round(valid_frac, 4)), 'plan': plan, 'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e,
+                'data': 'synthetic', 'config': workload_config(a, ilow), 'stacks_per_gpu': B, 'valid_pixel_fraction': round(valid_frac, 4),
+                'plan': plan, 'roofline': roofline, 'cpu_baseline': cpu, 'parity_check': parity, 'e2e': e2e,
                 'gpu_launches': int(launches_per_step * a.steps), 'clocks': clocks}
         print(json.dumps(line))
     if world > 1:

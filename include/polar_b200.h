@@ -71,7 +71,8 @@ typedef struct pb_params {
 } pb_params;
 
 /* Device output buffers of one analysis (any pointer may be NULL = not wanted).
- * Map element type is float, or double with PB_FLAG_OUT_F64. */
+ * Map element type is float, or double with PB_FLAG_OUT_F64. Any alignment natural for the element type is accepted; the
+ * vectorised kernels are used when every map is 16-byte aligned (mask: 4-byte), as torch / cudaMalloc allocations are. */
 typedef struct pb_outputs {
     void *var[PB_MAX_VARS];    /* [H,W] each, in the reference's datastack.vars order */
     void *intmap;              /* [H,W] a0 under the final mask (PP:3052-3053) */

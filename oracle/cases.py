@@ -30,7 +30,7 @@ def _rois():
 def _c(name, stack, **kw):
     d = dict(name=name, stack=stack, method='1PF', dark=480.0, ilow=0.0, offset_angle=0.0, polar_dir='clockwise',
              bins=(1, 1), rotation=(0.0, 0.0, 0.0), removed_intensity=0, disk=DISK_NODIST,
-             calib_label='no distortions', rois=None, per_roi=False, for_calib=True, edge=False, nbins=60)
+             calib_label='no distortions', rois=None, per_roi=False, for_calib=True, edge=False, nbins=60, mask=False)
     d.update(kw)
     return d
 
@@ -55,6 +55,8 @@ def all_cases():
     c.append(_c('1pf_fracdark', g1, dark=480.5, bins=(3, 3)))
     c.append(_c('1pf_rois', g1, rois=_rois(), per_roi=True, bins=(3, 3)))
     c.append(_c('1pf_rois_union', g1, rois=_rois(), per_roi=False, bins=(2, 2)))
+    c.append(_c('1pf_mask', g1, bins=(3, 3), ilow=30000.0, mask=True))
+    c.append(_c('1pf_mask_rois', g1, rois=_rois(), per_roi=True, mask=True))
     c.append(_c('1pf_noncalib', g1, bins=(3, 3), for_calib=False, rotation=(10.0, 5.0, 40.0), edge=True))
     g2 = ('4harm', dict(H=H, W=W, N=36, seed=0))
     g2d = ('4harm', dict(H=H, W=W, N=36, seed=1, dark=100))
@@ -98,3 +100,14 @@ def make_edge(shape):
     band = (np.abs(yy - shape[0] / 2) < 8)
     e[band] = (37.0 + 3.0 * xx[band]) % 180
     return e
+
+
+def make_mask_image(shape):
+    """A grey-level mask image as the reference reads it from '<stack name>.png' (PP:2082-2094): 0 = excluded, anything else
+    kept (the reference divides by the maximum and tests != 0)."""
+    yy, xx = np.indices(shape)
+    im = np.full(shape, 255, dtype=np.uint8)
+    im[(yy - shape[0] * 0.4) ** 2 + (xx - shape[1] * 0.55) ** 2 < (0.22 * min(shape)) ** 2] = 0      # a hole
+    im[:, : shape[1] // 7] = 0                                                                          # a dark band
+    im[shape[0] // 2:, shape[1] // 2:] = 90                                                             # grey, still kept
+    return im

@@ -23,7 +23,8 @@ ROOT = Path(__file__).resolve().parent.parent
 GOLD = ROOT / 'tests' / 'golden'
 
 
-def main():
+def main(only=None):
+    """only: iterable of case names to (re)generate; the other fixtures and their index entries are left as they are."""
     ref = rl.reference_dir()
     (GOLD / 'calib').mkdir(parents=True, exist_ok=True)
     (GOLD / 'cases').mkdir(parents=True, exist_ok=True)
@@ -33,15 +34,18 @@ def main():
                             PsiTest=np.asarray(d['PsiTest'], dtype=np.float64), NbMapValues=int(d['NbMapValues']))
     for k in ('Calib_th_2D', 'Calib_th_3D', 'Calib_20231009_2D'):
         np.save(GOLD / 'calib' / (k + '.npy'), np.genfromtxt(str(ref / 'calibration' / (k + '.txt')), dtype=np.float64))
-    index = {}
+    idx_file = GOLD / 'cases' / 'index.json'
+    index = json.loads(idx_file.read_text()) if (only and idx_file.exists()) else {}
     for c in cases.all_cases():
+        if only and c['name'] not in only:
+            continue
         v = cases.make_stack(c['stack'])
         edge = cases.make_edge(v.shape[1:]) if c['edge'] else None
         out = rl.run_reference(v, c['method'], c['dark'], c['ilow'], c['offset_angle'], c['polar_dir'], c['bins'],
                                c['rotation'], c['removed_intensity'],
                                disk=str(ref / 'diskcones' / (c['disk'] + '.mat')), calib_label=c['calib_label'],
                                rois=c['rois'], per_roi=c['per_roi'], for_calib=c['for_calib'], edge_contours=edge,
-                               nbins=c['nbins'])
+                               nbins=c['nbins'], mask_image=cases.make_mask_image(v.shape[1:]) if c['mask'] else None)
         arrs = dict(values=v, intensity=out['intensity'], intmap=out['intmap'], roi_map=out['roi_map'])
         for name, val in out['vars'].items():
             arrs['var_' + name] = val
@@ -60,4 +64,5 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    import sys
+    main(set(sys.argv[1:]) or None)

@@ -195,7 +195,7 @@ def make_app(method='1PF', dark=0.0, ilow=0.0, offset_angle=0.0, polar_dir='cloc
 def run_reference(values: np.ndarray, method='1PF', dark=0.0, ilow=0.0, offset_angle=0.0,
                   polar_dir='clockwise', bins=(1, 1), rotation=(0.0, 0.0, 0.0), removed_intensity=0,
                   disk=None, calib_label='no distortions', rois=None, per_roi=False, for_calib=True,
-                  reference_angle=None, edge_contours=None, nbins=60, var_ranges=None):
+                  reference_angle=None, edge_contours=None, nbins=60, var_ranges=None, mask_image=None):
     """Run the reference's own code on one stack `values` [N,H,W]. Returns a dict of results.
 
     for_calib=True goes through `Polarimetry.analyze_stack` (PP:2948) and returns the stats rows;
@@ -208,6 +208,14 @@ def run_reference(values: np.ndarray, method='1PF', dark=0.0, ilow=0.0, offset_a
     app = make_app(method, dark, ilow, offset_angle, polar_dir, bins, rotation, removed_intensity, disk,
                    calib_label, per_roi, 'ROI' if rois else 'Thresholding')
     stack = pc.Stack(Path('/tmp/synthetic.tif'))
+    if mask_image is not None:
+        # option 'Mask' (PP:2084): the reference opens <maskfolder>/<stack name>.png with PIL and divides by its maximum
+        import tempfile
+        import cv2
+        folder = Path(tempfile.mkdtemp(prefix='pb_mask_'))
+        cv2.imwrite(str(folder / 'synthetic.png'), np.asarray(mask_image, dtype=np.uint8))
+        app.option = _Var('Mask')
+        app.maskfolder = folder
     stack.values = values
     stack.nangle, stack.height, stack.width = values.shape
     app.stack = stack

@@ -55,7 +55,12 @@ class Calibration:
     """Disk-cone table (1PF) or inverse polarization matrix (4POLAR): the data side of the reference's
     `Calibration` (PC:411-464). The tables themselves are the user's / the reference's data files."""
 
+    _next_uid = 0
+
     def __init__(self, rho_table=None, psi_table=None, n: Optional[int] = None, invK=None, name: str = ''):
+        # never-recycled identity for the engine's upload cache (id() is reused as soon as an object is freed)
+        Calibration._next_uid += 1
+        self.uid = Calibration._next_uid
         self.name = name
         self.rho_table = None if rho_table is None else np.ascontiguousarray(rho_table, dtype=np.float64)
         self.psi_table = None if psi_table is None else np.ascontiguousarray(psi_table, dtype=np.float64)
@@ -200,9 +205,10 @@ class Engine:
         if p.method == '1PF':
             if calib is None or calib.rho_table is None:
                 raise ValueError('1PF needs a disk-cone Calibration')
-            key = ('disk', id(calib))
+            key = ('disk', calib.uid)
             if key != self._key_calib:
                 n = calib.grid.size
+                self._key_calib = None           # a failed upload must not look cached
                 self._ck(self.lib.pb_set_diskcone(self._ctx, _ptr(calib.rho_table), _ptr(calib.psi_table), n, _ptr(calib.grid)), 'pb_set_diskcone')
                 self._key_calib = key
         elif p.method.startswith('4POLAR'):
@@ -219,6 +225,7 @@ class Engine:
         if key != self._key_hist:
             edges = np.ascontiguousarray(np.stack([np.linspace(p.ranges[n][0], p.ranges[n][1], p.nbins + 1) for n in names]))
             is_rho = np.array([int(n == 'Rho') for n in names], dtype=np.int32)
+            self._key_hist = None                # a failed upload must not look cached
             self._ck(self.lib.pb_set_hist(self._ctx, len(names), p.nbins, _ptr(edges), _ptr(is_rho)), 'pb_set_hist')
             self._key_hist = key
 

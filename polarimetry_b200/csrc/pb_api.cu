@@ -162,7 +162,7 @@ int pb_destroy(pb_ctx *ctx) {
     if (!ctx) return PB_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
+    cudaFree(ctx->lut_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); }
     if (ctx->hist_pinned) cudaFreeHost(ctx->hist_pinned);
@@ -176,12 +176,8 @@ long pb_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, const double *grid) {
     if (!ctx || !rho || !psi || !grid || n < 2) return fail(ctx, PB_ERR_ARG, "pb_set_diskcone: bad argument");
-    CK(cudaSetDevice(ctx->device));
-    std::vector<double2> t((size_t)n * n);
-    for (size_t k = 0; k < t.size(); ++k) { t[k].x = rho[k]; t[k].y = psi[k]; }
-    CK(cudaDeviceSynchronize());
-    if (ctx->lut_dev) { cudaFree(ctx->lut_dev); cudaFree(ctx->grid_dev); cudaFree(ctx->hy_dev); ctx->lut_dev = nullptr; ctx->grid_dev = nullptr; ctx->hy_dev = nullptr; }
-    // the cell search corrects an arithmetic guess by at most one cell: the grid must be (numerically) uniform, as the
+    // validate first: a rejected call leaves the previous table in place.
+    // The cell search corrects an arithmetic guess by at most one cell: the grid must be (numerically) uniform, as the
     // reference's always is (np.linspace(-1, 1, NbMapValues), PC:463)
     {
         const double step = (grid[n - 1] - grid[0]) / (double)(n - 1);
@@ -195,12 +191,22 @@ int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, co
         hy[k].y = 1.0 / hy[k].x;               // correctly rounded reciprocal
         if (!(hy[k].x > 0.0)) return fail(ctx, PB_ERR_ARG, "pb_set_diskcone: grid must be strictly increasing");
     }
-    CK(cudaMalloc(&ctx->hy_dev, sizeof(double2) * hy.size()));
-    CK(cudaMemcpy(ctx->hy_dev, hy.data(), sizeof(double2) * hy.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&ctx->lut_dev, sizeof(double2) * t.size()));
-    CK(cudaMalloc(&ctx->grid_dev, sizeof(double) * n));
-    CK(cudaMemcpy(ctx->lut_dev, t.data(), sizeof(double2) * t.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->grid_dev, grid, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double2> t((size_t)n * n);
+    for (size_t k = 0; k < t.size(); ++k) { t[k].x = rho[k]; t[k].y = psi[k]; }
+    // one allocation: table | grid | (h, 1/h); uploaded before the old one is released
+    const size_t b_t = sizeof(double2) * t.size(), b_g = (sizeof(double) * n + 15) & ~(size_t)15, b_h = sizeof(double2) * hy.size();
+    char *blk = nullptr;
+    CK(cudaMalloc(&blk, b_t + b_g + b_h));
+    cudaError_t e_ = cudaMemcpy(blk, t.data(), b_t, cudaMemcpyHostToDevice);
+    if (e_ == cudaSuccess) e_ = cudaMemcpy(blk + b_t, grid, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e_ == cudaSuccess) e_ = cudaMemcpy(blk + b_t + b_g, hy.data(), b_h, cudaMemcpyHostToDevice);
+    if (e_ == cudaSuccess && ctx->lut_dev) e_ = cudaDeviceSynchronize();   // kernels already enqueued may still read the old table
+    if (e_ != cudaSuccess) { cudaFree(blk); ctx->err = std::string("pb_set_diskcone: ") + cudaGetErrorString(e_); return PB_ERR_CUDA; }
+    if (ctx->lut_dev) cudaFree(ctx->lut_dev);
+    ctx->lut_dev = reinterpret_cast<double2 *>(blk);
+    ctx->grid_dev = reinterpret_cast<double *>(blk + b_t);
+    ctx->hy_dev = reinterpret_cast<double2 *>(blk + b_t + b_g);
     ctx->lut_n = n;
     ctx->grid_lo = grid[0]; ctx->grid_hi = grid[n - 1];
     return PB_OK;
@@ -244,9 +250,7 @@ int pb_set_basis(pb_ctx *ctx, int N, const double *c2, const double *s2, const d
 int pb_set_hist(pb_ctx *ctx, int n_vars, int nbins, const double *edges, const int32_t *is_rho) {
     if (!ctx || n_vars < 0 || n_vars > PB_MAX_VARS || nbins < 1 || nbins > PB_MAX_BINS || (n_vars && (!edges || !is_rho)))
         return fail(ctx, PB_ERR_ARG, "pb_set_hist: bad argument");
-    CK(cudaSetDevice(ctx->device));
-    CK(cudaDeviceSynchronize());
-    if (ctx->edges_dev) { cudaFree(ctx->edges_dev); ctx->edges_dev = nullptr; }
+    // validate first: a rejected call leaves the previous histogram set-up untouched
     // the bin search corrects an arithmetic guess by at most one bin: edges must be uniform (np.linspace, PC:367)
     for (int v = 0; v < n_vars; ++v) {
         const double *e = edges + (size_t)v * (nbins + 1);
@@ -255,10 +259,21 @@ int pb_set_hist(pb_ctx *ctx, int n_vars, int nbins, const double *edges, const i
             if (!(step > 0.0) || !(fabs(e[k] - (e[0] + k * step)) <= 0.25 * step))
                 return fail(ctx, PB_ERR_UNSUPPORTED, "pb_set_hist: edges must be uniform and increasing (np.linspace), as in Variable.histo");
     }
+    CK(cudaSetDevice(ctx->device));
+    double *dev = nullptr;
+    if (n_vars) {
+        CK(cudaMalloc(&dev, sizeof(double) * n_vars * (nbins + 1)));
+        cudaError_t e_ = cudaMemcpy(dev, edges, sizeof(double) * n_vars * (nbins + 1), cudaMemcpyHostToDevice);
+        if (e_ != cudaSuccess) { cudaFree(dev); ctx->err = std::string("pb_set_hist: ") + cudaGetErrorString(e_); return PB_ERR_CUDA; }
+    }
+    // swap: kernels already enqueued may still read the old edges
+    if (ctx->edges_dev) {
+        cudaError_t e_ = cudaDeviceSynchronize();
+        if (e_ != cudaSuccess) { cudaFree(dev); ctx->err = std::string("pb_set_hist: ") + cudaGetErrorString(e_); return PB_ERR_CUDA; }
+        cudaFree(ctx->edges_dev);
+    }
+    ctx->edges_dev = dev;
     ctx->n_vars = n_vars; ctx->nbins = nbins; ctx->is_rho_bits = 0;
-    if (n_vars == 0) return PB_OK;
-    CK(cudaMalloc(&ctx->edges_dev, sizeof(double) * n_vars * (nbins + 1)));
-    CK(cudaMemcpy(ctx->edges_dev, edges, sizeof(double) * n_vars * (nbins + 1), cudaMemcpyHostToDevice));
     for (int v = 0; v < n_vars; ++v) {
         const double *e = edges + (size_t)v * (nbins + 1);
         ctx->inv_w[v] = (double)nbins / (e[nbins] - e[0]);
@@ -306,7 +321,7 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     a.method = p->method;
     a.do_sqrt = p->method == PB_CARS;
     const int nv = method_nvars(p->method);
-    a.n_vars = (ctx->n_vars >= nv) ? nv : 0;   // histograms only if edges were given for every primary variable
+    a.n_vars = (ctx->n_vars >= nv && ctx->edges_dev) ? nv : 0;   // histograms only if edges were given for every primary variable
     a.nbins = ctx->nbins > 0 ? ctx->nbins : 1;
     a.n_groups = ctx->n_groups; a.n_rois = ctx->n_rois;
     a.flags = p->flags;
@@ -328,6 +343,17 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     memcpy(a.invk, ctx->invk, sizeof(a.invk));
     a.grid_lo = ctx->grid_lo; a.grid_hi = ctx->grid_hi; a.half_nm1 = 0.5 * (double)(ctx->lut_n - 1);
     a.simple = 0;   // set by the callers once roi_bits / mask_in are known
+}
+
+// vector stores of the per-pixel kernels need 16-byte aligned maps (4-byte aligned mask); otherwise the scalar kernels run
+static int outs_aligned(const pb_outputs *o, int n) {
+    uintptr_t acc = 0, m = 0;
+    for (int s = 0; s < n; ++s) {
+        for (int v = 0; v < PB_MAX_VARS; ++v) acc |= (uintptr_t)o[s].var[v];
+        acc |= (uintptr_t)o[s].intmap | (uintptr_t)o[s].intensity | (uintptr_t)o[s].rho_angle | (uintptr_t)o[s].rho_contour;
+        m |= (uintptr_t)o[s].mask;
+    }
+    return (acc % 16 == 0) && (m % 4 == 0);
 }
 
 // copy n output descriptors into the device ring; returns device pointer
@@ -432,6 +458,7 @@ int pb_compute_fields(pb_ctx *ctx, const pb_params *p, const double *field, uint
     if ((rc = push_outs(ctx, &o, 1, st, &od))) return rc;
     a.stack = field; a.stack_stride = 0; a.from_field = 1; a.do_sqrt = 0;
     a.mask_in = mask; a.roi_bits = roi_bits; a.edge = edge; a.outs = od;
+    a.out_aligned = outs_aligned(&o, 1);
     return launch_pixel(ctx, p, a, PB_F64, 1, st);
 }
 
@@ -446,6 +473,7 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
     fill_args(ctx, p, a);
     a.roi_bits = roi_bits; a.edge = edge;
     a.simple = (!roi_bits && ctx->n_rois == 0 && ctx->n_groups == 1) ? 1 : 0;
+    a.out_aligned = outs_aligned(outs_host, n_stacks);
     const long long P = a.P;
     const std::string plan = plan_name(ctx, p);
     const pb_outputs *od;

@@ -430,7 +430,7 @@ cudaError_t launch_harm_t(const PixArgs &a_in, const typename BasisSel<NH>::type
     const int threads = 128;
     PixArgs a = a_in;
     // PX = 4 needs every plane (and every stack) to start on a 4-element boundary
-    const bool vec = (a.P % 4 == 0) && (a.stack_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.stack) % (4 * sizeof(T))) == 0);
+    const bool vec = (a.P % 4 == 0) && (a.stack_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.stack) % (4 * sizeof(T))) == 0) && a.out_aligned;
     // epilogue queue (results overwrite the entries) behind the histograms: per pixel of the CTA 2 + 2 NH doubles, a 16-bit
     // index and a mask byte; then the queue counter
     smem = (smem + 15) & ~(size_t)15;

@@ -75,7 +75,7 @@ def test_analyze_matches_reference(eng, name):
     c = util.CASE_BY_NAME[name]
     g = util.golden(name)
     edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
-    res = eng.analyze(g['values'], params_for(c), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    res = eng.analyze(g['values'], params_for(c), calib_for(c), c['rois'], c['per_roi'], util.base_mask_for(c, g['values'].shape[1:]), edge)
     check_against_golden(c, res, g, exact_maps=True)
 
 
@@ -84,7 +84,7 @@ def test_unfused_kernels_match_reference(eng, name):
     c = util.CASE_BY_NAME[name]
     g = util.golden(name)
     edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
-    res = eng.analyze(g['values'], params_for(c, force_unfused=True), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    res = eng.analyze(g['values'], params_for(c, force_unfused=True), calib_for(c), c['rois'], c['per_roi'], util.base_mask_for(c, g['values'].shape[1:]), edge)
     assert res.plan == 'unfused'
     check_against_golden(c, res, g, exact_maps=True)
 
@@ -94,7 +94,7 @@ def test_exact_chi2_flag_gives_same_decisions(eng, name):
     c = util.CASE_BY_NAME[name]
     g = util.golden(name)
     edge = cases.make_edge(g['values'].shape[1:]) if c['edge'] else None
-    res = eng.analyze(g['values'], params_for(c, exact_chi2=True), calib_for(c), c['rois'], c['per_roi'], None, edge)
+    res = eng.analyze(g['values'], params_for(c, exact_chi2=True), calib_for(c), c['rois'], c['per_roi'], util.base_mask_for(c, g['values'].shape[1:]), edge)
     check_against_golden(c, res, g, exact_maps=True)
 
 

@@ -16,8 +16,8 @@ NAMES = [c['name'] for c in util.CASES]
 def _run(mod, c, v, edge):
     p = util.params_for(c)
     if mod is rs:
-        return rs.analyze_stack(v, p, util.calib_for(c), c['rois'], c['per_roi'], None, edge, c['for_calib'])
-    return ct.analyze_stack(v, p, util.calib_for(c), c['rois'], c['per_roi'], None, edge)
+        return rs.analyze_stack(v, p, util.calib_for(c), c['rois'], c['per_roi'], util.base_mask_for(c, v.shape[1:]), edge, c['for_calib'])
+    return ct.analyze_stack(v, p, util.calib_for(c), c['rois'], c['per_roi'], util.base_mask_for(c, v.shape[1:]), edge)
 
 
 @pytest.mark.parametrize('name', NAMES)

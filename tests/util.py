@@ -54,3 +54,8 @@ def circ_diff(a, b, period=180.0):
     """Circular distance for rho-like maps (NaN positions must agree, checked separately)."""
     d = np.abs(a - b)
     return np.minimum(d, period - d)
+
+
+def base_mask_for(c, shape):
+    """The mask image of a 'Mask'-option case (PP:2082-2094), or None."""
+    return cases.make_mask_image(shape) if c.get('mask') else None
