@@ -6,6 +6,17 @@ cudaError_t pb_march_u16_nh1(const PixArgs &a, const Basis1 &bs, const pb_params
 cudaError_t pb_march_u16_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
 cudaError_t pb_march_u8_nh1(const PixArgs &a, const Basis1 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
 cudaError_t pb_march_u8_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
+cudaError_t pb_march_tma_nh1(const PixArgs &a, const Basis1 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_1.cu
+cudaError_t pb_march_tma_nh2(const PixArgs &a, const Basis2 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_2.cu
+
+// The TMA kernel (pb_march_tma.cuh) takes the common case: uint16 stacks, square windows 2..8, rows that are a multiple of 16 bytes
+// and a 16-byte aligned stack (the tensor map's stride / address rules). PB_MARCH_TMA=0 keeps the register-staged loader.
+static bool tma_eligible(const PixArgs &a, const pb_params *p) {
+    static const bool on = [] { const char *e = getenv("PB_MARCH_TMA"); return !e || atoi(e) != 0; }();
+    if (!on || p->dtype != PB_U16 || p->bin_h != p->bin_w || p->bin_w < 2 || p->bin_w > 8) return false;
+    if (a.W % 8 != 0 || a.W < 16 || a.H < 1 || (reinterpret_cast<uintptr_t>(a.stack) & 15) != 0 || (a.stack_stride % 8) != 0) return false;
+    return true;
+}
 
 
 // The march kernel covers: harmonic modalities without sqrt (1PF, SRS, SHG, 2PF), integer stacks, integer-valued
@@ -37,13 +48,18 @@ bool pb_march_supported(const pb_params *p) {
 
 cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches) {
     cudaError_t e;
+    const bool tma_ok = tma_eligible(a, p);
     if (p->method == PB_1PF) {
         Basis1 b1;
         memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));
         memcpy(b1.kc2, bs.kc2, sizeof(b1.kc2)); memcpy(b1.ks2, bs.ks2, sizeof(b1.ks2));
-        e = p->dtype == PB_U8 ? pb_march_u8_nh1(a, b1, p, n_stacks, st) : pb_march_u16_nh1(a, b1, p, n_stacks, st);
+        e = tma_ok ? pb_march_tma_nh1(a, b1, p->bin_w, n_stacks, st) : cudaErrorInvalidConfiguration;
+        if (e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported)      // shape outside the TMA kernel's plan: register-staged loader
+            e = p->dtype == PB_U8 ? pb_march_u8_nh1(a, b1, p, n_stacks, st) : pb_march_u16_nh1(a, b1, p, n_stacks, st);
     } else {
-        e = p->dtype == PB_U8 ? pb_march_u8_nh2(a, bs, p, n_stacks, st) : pb_march_u16_nh2(a, bs, p, n_stacks, st);
+        e = tma_ok ? pb_march_tma_nh2(a, bs, p->bin_w, n_stacks, st) : cudaErrorInvalidConfiguration;
+        if (e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported)
+            e = p->dtype == PB_U8 ? pb_march_u8_nh2(a, bs, p, n_stacks, st) : pb_march_u16_nh2(a, bs, p, n_stacks, st);
     }
     if (e == cudaSuccess && launches) ++*launches;
     return e;

@@ -27,7 +27,7 @@ def g1_ilow(intensity):
     return float('{:.0f}'.format(np.percentile(intensity, 20.0)))
 
 
-def compare(res, ref, exact_maps):
+def compare(res, ref, exact_maps, p=None):
     assert util.eq(res.mask.cpu().numpy().astype(bool), ref['mask'])
     assert util.eq(res.intensity.cpu().numpy(), ref['intensity'])
     assert util.eq(res.intmap.cpu().numpy(), ref['intmap'])
@@ -43,7 +43,19 @@ def compare(res, ref, exact_maps):
             assert d.max(initial=0.0) <= (1e-9 if v.name in ANGLE_VARS else 1e-12), (v.name, d.max())
     assert set(res.hist) == set(ref['hist'])
     for k, h in res.hist.items():
-        assert util.eq(h, ref['hist'][k]), k
+        if exact_maps:
+            assert util.eq(h, ref['hist'][k]), k
+            continue
+        # transcendental outputs: exact wherever the reference value is farther than the map tolerance from a bin edge
+        # (util.hist_explained_by_ties), and exactly the histogram of the device's own fp64 map
+        name = k[0]
+        vmin, vmax = p.ranges[name]
+        edges = np.linspace(vmin, vmax, p.nbins + 1)
+        tol = 1e-9 if name in ANGLE_VARS else 1e-12
+        ok, n_ties, n_moved = util.hist_explained_by_ties(h, ref['hist'][k], ref['vars'][name], edges, tol, name == 'Rho', float(p.rotation[1]))
+        assert ok, (k, n_ties, n_moved, h - ref['hist'][k])
+        own = rs.histo(res.get_var(name).values.cpu().numpy(), None, name, vmin, vmax, float(p.rotation[1]), p.nbins)[0]
+        assert util.eq(h, own), (k, 'device histogram vs histogram of the device map')
 
 
 @pytest.mark.parametrize('bins', [(3, 3), (1, 1)])
@@ -73,7 +85,7 @@ def test_4harmonic_2048x2048x36_configs1(eng, method, bins):
     res = eng.analyze(v, AnalysisParams(**p))
     ref = rs.analyze_stack(v, rs.Params(**p), None, want_stats=False)
     assert ref['mask'].mean() > 0.5
-    compare(res, ref, exact_maps=False)
+    compare(res, ref, exact_maps=False, p=rs.Params(**p))
 
 
 def test_4polar3d_4x2048x2048_configs2(eng):
@@ -84,7 +96,7 @@ def test_4polar3d_4x2048x2048_configs2(eng):
         res = eng.analyze(v, AnalysisParams(**p), Calibration.from_K(K))
         ref = rs.analyze_stack(v, rs.Params(**p), rs.Calib.from_K(K), want_stats=False)
         assert ref['mask'].mean() > 0.3
-        compare(res, ref, exact_maps=False)
+        compare(res, ref, exact_maps=False, p=rs.Params(**p))
 
 
 def test_two_temporary_calibrations_back_to_back(eng):

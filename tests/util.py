@@ -59,3 +59,30 @@ def circ_diff(a, b, period=180.0):
 def base_mask_for(c, shape):
     """The mask image of a 'Mask'-option case (PP:2082-2094), or None."""
     return cases.make_mask_image(shape) if c.get('mask') else None
+
+
+def hist_explained_by_ties(h_got, h_ref, ref_values, edges, tol, is_rho=False, rotation_fig=0.0):
+    """Tie-aware histogram comparison for variables that go through a transcendental (atan2 / acos / hypot / cos).
+    Where the reference's value lies within `tol` of a bin edge its bin is decided by the last bits of the host's libm / SVML
+    (numpy's AVX-512 arctan2 differs from glibc's by 1 ulp on 7 % of random inputs), so it is not a property of the algorithm.
+    Exact integer data produce such values structurally (e.g. 4POLAR: equal counts in two channels -> rho = 45 deg up to rounding).
+    Requirement: the net number of values that crossed each edge (cumulative count difference) is at most the number of
+    reference values within `tol` of that edge; everything else must match exactly. Returns (ok, n_ties, n_moved)."""
+    d = np.asarray(ref_values, dtype=np.float64)
+    d = d[np.isfinite(d)]
+    if is_rho:
+        d = np.mod(2 * (d + rotation_fig), 360) / 2
+    edges = np.asarray(edges, dtype=np.float64)
+    ties = np.array([np.count_nonzero(np.abs(d - e) <= tol) for e in edges])
+    diff = np.asarray(h_got, dtype=np.int64) - np.asarray(h_ref, dtype=np.int64)
+    # crossed[k] = values counted below edge k+1 by `got` but not by `ref` (k = 0 .. nbins-1; the last one concerns the closed top edge)
+    crossed = np.cumsum(diff)
+    lower = np.concatenate(([0], crossed[:-1]))          # net inflow through the bottom edge of the histogram is bounded by ties[0]
+    ok = True
+    for k in range(len(diff)):
+        # values entering / leaving bin k can only come through its two edges
+        if abs(diff[k]) > ties[k] + ties[k + 1]:
+            ok = False
+    if abs(int(diff.sum())) > ties[0] + ties[-1]:
+        ok = False
+    return ok, int(ties.sum()), int(np.abs(diff).sum() // 2 + abs(int(diff.sum())))
