@@ -843,15 +843,8 @@ def binning(self, field: np.ndarray) -> np.ndarray:
     return field
 
 
-def compute_fields(field: np.ndarray, datastack, mask: np.ndarray, method: str = '1PF', polar_dir: str = 'clockwise',
-                   offset_angle: float = 0, calibration=None, edge_contours=None, reference_angle: float = 0,
-                   rotation: float = 0, for_calib: bool = False, chi2threshold: float = 500, _Variable=None):
-    """Drop-in for the module-level compute_fields (PP:2981-3078): same arguments, same side effects
-    (`mask` updated in place; `datastack.vars/.intmap/.xmap/.ymap/.field/.field_fit/.chi2` filled)."""
-    eng = default_engine()
-    p = AnalysisParams(method=method, polar_dir=polar_dir, offset_angle=float(offset_angle),
-                       rotation=(float(rotation), 0.0, float(reference_angle)), chi2threshold=float(chi2threshold))
-    cal = None
+def _pb_calibration(calibration, method: str):
+    """The reference's Calibration object (PC:411-464) -> this package's Calibration, cached on the object."""
     if method == '1PF':
         cal = getattr(calibration, '_pb_calib', None)
         if cal is None:
@@ -860,8 +853,21 @@ def compute_fields(field: np.ndarray, datastack, mask: np.ndarray, method: str =
                 calibration._pb_calib = cal
             except Exception:
                 pass
-    elif method.startswith('4POLAR'):
-        cal = Calibration(invK=calibration.invKmat)
+        return cal
+    if method.startswith('4POLAR'):
+        return Calibration(invK=calibration.invKmat)
+    return None
+
+
+def compute_fields(field: np.ndarray, datastack, mask: np.ndarray, method: str = '1PF', polar_dir: str = 'clockwise',
+                   offset_angle: float = 0, calibration=None, edge_contours=None, reference_angle: float = 0,
+                   rotation: float = 0, for_calib: bool = False, chi2threshold: float = 500, _Variable=None):
+    """Drop-in for the module-level compute_fields (PP:2981-3078): same arguments, same side effects
+    (`mask` updated in place; `datastack.vars/.intmap/.xmap/.ymap/.field/.field_fit/.chi2` filled)."""
+    eng = default_engine()
+    p = AnalysisParams(method=method, polar_dir=polar_dir, offset_angle=float(offset_angle),
+                       rotation=(float(rotation), 0.0, float(reference_angle)), chi2threshold=float(chi2threshold))
+    cal = _pb_calibration(calibration, method)
     res = eng.compute_fields(field, mask, p, cal, edge_contours, want_fit=not for_calib)
     mk = (lambda n, v: _Variable(n, values=v)) if _Variable is not None else Variable
     datastack.vars = [mk(v.name, v.values.cpu().numpy()) for v in res.vars]
@@ -880,16 +886,198 @@ def compute_fields(field: np.ndarray, datastack, mask: np.ndarray, method: str =
     return datastack
 
 
-def install(pypolar_module, classes_module=None) -> None:
-    """Rebind the hot-path seams of an imported reference (`import PyPOLAR`) to this package."""
-    Var = getattr(pypolar_module, 'Variable', None)
+class LazyMaps:
+    """`datastack.field / .field_fit / .chi2` of the fused S4 path (PP:3073-3077). The reference materialises two float64 [N,H,W]
+    arrays that only the individual-fit viewer reads, one clicked pixel at a time (PP:2485-2494); here they are produced on first
+    use from the raw stack (pb_field + pb_fit_maps) and then behave like the NumPy arrays the reference stores."""
+
+    def __init__(self, engine: Engine, values, params: AnalysisParams, mask: torch.Tensor):
+        self._eng, self._values, self._p, self._mask, self._cache = engine, values, params, mask, None
+
+    def _get(self):
+        if self._cache is None:
+            f = self._eng.field(self._values, self._p)
+            N, H, W = f.shape
+            self._eng._set_basis(N, self._p)
+            pp = self._eng._params(self._p, 'float64', N, H, W)
+            fit = torch.empty_like(f)
+            chi2 = torch.empty((H, W), dtype=torch.float64, device=f.device)
+            m = self._mask.to(torch.uint8).contiguous()
+            self._eng._ck(self._eng.lib.pb_fit_maps(self._eng._ctx, C.byref(pp), f.data_ptr(), m.data_ptr(), fit.data_ptr(), chi2.data_ptr(),
+                                                    self._eng._stream()), 'pb_fit_maps')
+            f = torch.where(m.bool()[None], f, torch.full_like(f, float('nan')))          # PP:3074
+            self._cache = {'field': f.cpu().numpy(), 'field_fit': fit.cpu().numpy(), 'chi2': chi2.cpu().numpy()}
+            self._values = None
+        return self._cache
+
+    def view(self, key: str):
+        return _LazyArray(self, key)
+
+
+class _LazyArray:
+    """NumPy-like view on one of the LazyMaps arrays: indexing, np.asarray(), .shape / .ndim / .dtype trigger the computation."""
+
+    def __init__(self, owner: LazyMaps, key: str):
+        self._owner, self._key = owner, key
+
+    def _a(self) -> np.ndarray:
+        return self._owner._get()[self._key]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._a()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self._a()[idx]
+
+    def __setitem__(self, idx, value):
+        self._a()[idx] = value
+
+    def __len__(self):
+        return len(self._a())
+
+    def __getattr__(self, name):
+        return getattr(self._a(), name)
+
+
+def analyze_stack(self, datastack, for_calib: bool = False, _Variable=None):
+    """Drop-in for Polarimetry.analyze_stack (PP:2948-2979), the FUSED seam S4: the GUI state is pulled exactly where the reference
+    pulls it (PP:2949-2968), the raw `self.stack.values` goes through the fused kernels (one pass over the stack: pre-processing,
+    binning, compute_fields), `datastack` is filled as compute_fields fills it, and the reference's own `return_vecexcel` /
+    `plot_data` / `save_data` run on the result. `self` is the reference application object."""
+    eng = default_engine()
+    roi_map, _mask = self.compute_roi_map(datastack)                       # PP:2949 (also the per_roi.deselect() side effect, PP:2873-2874)
+    method = self.method.get()                                             # PP:2950
+    datastack.dark = float(self.dark.get())                                # PP:2951
+    datastack.method = method                                              # PP:2952
+    calibration = self.CD if method in ['1PF', '4POLAR 2D', '4POLAR 3D'] else None      # PP:2958-2961
+    if hasattr(self, 'edge_contours'):                                     # PP:2963-2966
+        edge_contours, datastack.xct, datastack.yct = self.define_rho_ct(self.edge_contours)
+    else:
+        edge_contours = None
+    p = AnalysisParams(method=method, dark=datastack.dark, removed_intensity=float(self.removed_intensity),
+                       bins=tuple(int(sb.get()) for sb in self.bin_spinboxes),                     # PP:2943
+                       polar_dir=self.polar_dir.get(), offset_angle=float(self.offset_angle.get()),
+                       rotation=(float(self.rotation[0].get()), 0.0, float(self.rotation[2].get())),
+                       ilow=float(self.ilow.get()))                                                # PP:2876
+    base = self.get_mask(datastack, False)                                 # PP:2890 (the PNG mask or ones; no second pop-up)
+    res = eng.analyze(self.stack.values, p, _pb_calibration(calibration, method), datastack.rois, bool(self.per_roi.get()),
+                      None if np.all(np.asarray(base) != 0) else base, edge_contours, want_hist=False)
+    mk = (lambda n, v: _Variable(n, values=v)) if _Variable is not None else Variable
+    datastack.vars = [mk(v.name, v.values.cpu().numpy()) for v in res.vars]
+    datastack.intmap = res.intmap.cpu().numpy()
+    if not for_calib:
+        datastack.xmap, datastack.ymap = res.xmap.cpu().numpy(), res.ymap.cpu().numpy()       # PP:3056-3058
+        if edge_contours is not None:                                                          # PP:3063
+            both = np.isfinite(datastack.vars[0].values) & np.isfinite(edge_contours)
+            datastack.xct[~both], datastack.yct[~both] = np.nan, np.nan
+        if not method.startswith('4POLAR'):                                                    # PP:3073-3077, on demand
+            lazy = LazyMaps(eng, self.stack.values, p, res.mask)
+            datastack.field, datastack.field_fit, datastack.chi2 = lazy.view('field'), lazy.view('field_fit'), lazy.view('chi2')
+    if for_calib:                                                          # PP:2969-2977
+        if self.per_roi.get():
+            result = []
+            for roi in datastack.rois:
+                if roi['select']:
+                    result.append(self.return_vecexcel(datastack, roi_map, roi=roi, simplify=True)[0])
+        else:
+            result = [self.return_vecexcel(datastack, roi_map, roi=[], simplify=True)[0]]
+        return result
+    self.plot_data(datastack, roi_map=roi_map)                             # PP:2978
+    self.save_data(datastack, roi_map=roi_map)                             # PP:2979
+
+
+def histogram(a, bins=10, range=None, *args, **kwargs):
+    """Drop-in for the np.histogram call of Variable.histo (PC:369, seam S5): explicit uniform edges (np.linspace) and a float
+    array go to the device (pb_histo: [e_k, e_k+1), last bin closed, values outside dropped -- numpy's rule); anything else is
+    numpy's business. Returns (counts int64, bin_edges) like numpy."""
+    edges = np.asarray(bins)
+    arr = np.asarray(a)
+    if args or kwargs or edges.ndim != 1 or edges.size < 2 or edges.size - 1 > _cabi.PB_MAX_BINS or arr.dtype.kind != 'f' or arr.size == 0:
+        return np.histogram(a, bins, range, *args, **kwargs)
+    edges = np.ascontiguousarray(edges, dtype=np.float64)
+    step = (edges[-1] - edges[0]) / (edges.size - 1)
+    if not (step > 0) or np.any(np.abs(edges - (edges[0] + step * np.arange(edges.size))) > 0.25 * step):
+        return np.histogram(a, bins, range, *args, **kwargs)
+    eng = default_engine()
+    v = eng._to_device(np.ascontiguousarray(arr.ravel(), dtype=np.float64))
+    counts = torch.zeros(edges.size - 1, dtype=torch.int64, device=eng.device)
+    eng._ck(eng.lib.pb_histo(eng._ctx, v.data_ptr(), 1, None, v.numel(), 0, 0.0, 0, _ptr(edges), edges.size - 1, counts.data_ptr(), eng._stream()),
+            'pb_histo')
+    return counts.cpu().numpy(), edges
+
+
+class _NumpyWithDeviceHistogram:
+    """Stands in for the `np` name of pypolar_classes: every attribute is numpy's, except `histogram` (seam S5)."""
+
+    def __init__(self, numpy_module):
+        self.__dict__['_np'] = numpy_module
+
+    def __getattr__(self, name):
+        return histogram if name == 'histogram' else getattr(self.__dict__['_np'], name)
+
+
+_SEAMS = (('module', 'compute_fields'), ('Polarimetry', 'binning'), ('Polarimetry', 'analyze_stack'), ('Stack', 'get_intensity'),
+          ('Stack', 'compute_dark'), ('classes', 'np'))
+
+
+def install(pypolar_module, classes_module=None) -> dict:
+    """Rebind the hot-path seams of an imported reference (`import PyPOLAR, pypolar_classes`) to this package:
+    S1 compute_fields, S2 Polarimetry.binning, S3 Stack.get_intensity (+ Stack.compute_dark), S4 Polarimetry.analyze_stack (the
+    fused entry: what the Analysis button, the folder loop and the calibration sweep call, PP:898 / PP:2128 / PP:2133) and S5 the
+    np.histogram call of Variable.histo. Nothing touches the GPU until a rebound function is called. Returns the original
+    attributes for `uninstall`."""
+    import functools
+    import inspect
+    Var = getattr(pypolar_module, 'Variable', None) or getattr(classes_module, 'Variable', None)
+    stack_cls = getattr(classes_module, 'Stack', None) or getattr(pypolar_module, 'Stack', None)
+    saved = {'pypolar': pypolar_module, 'classes': classes_module, 'stack_cls': stack_cls, 'attrs': {}}
+
+    def rebind(owner, name, new, key):
+        old = getattr(owner, name, None)
+        saved['attrs'][key] = (owner, name, old)
+        if callable(old) and callable(new):
+            try:                                          # present the reference's own signature / name to introspection
+                new.__signature__ = inspect.signature(old)
+                new.__name__, new.__qualname__ = old.__name__, getattr(old, '__qualname__', old.__name__)
+            except (TypeError, ValueError):
+                pass
+        setattr(owner, name, new)
 
     def _cf(*a, **k):
         return compute_fields(*a, _Variable=Var, **k)
 
-    pypolar_module.compute_fields = _cf
-    pypolar_module.Polarimetry.binning = binning
-    stack_cls = getattr(classes_module, 'Stack', None) or getattr(pypolar_module, 'Stack', None)
+    def _as(self, datastack, for_calib=False):
+        return analyze_stack(self, datastack, for_calib, _Variable=Var)
+
+    def _binning(self, field):
+        return binning(self, field)
+
+    def _gi(self, dark=0.0, bin=[1, 1]):
+        return get_intensity(self, dark, bin)
+
+    def _cd(self, size_cell=20):
+        return compute_dark(self, size_cell)
+
+    functools.update_wrapper(_cf, compute_fields)
+    rebind(pypolar_module, 'compute_fields', _cf, 'S1')
+    rebind(pypolar_module.Polarimetry, 'binning', _binning, 'S2')
+    rebind(pypolar_module.Polarimetry, 'analyze_stack', _as, 'S4')
     if stack_cls is not None:
-        stack_cls.get_intensity = get_intensity
-        stack_cls.compute_dark = compute_dark
+        rebind(stack_cls, 'get_intensity', _gi, 'S3')
+        rebind(stack_cls, 'compute_dark', _cd, 'N2')
+    if classes_module is not None and hasattr(classes_module, 'np'):
+        rebind(classes_module, 'np', _NumpyWithDeviceHistogram(classes_module.np), 'S5')
+    return saved
+
+
+def uninstall(saved: dict) -> None:
+    """Undo `install` (restores the reference's own functions)."""
+    for owner, name, old in saved['attrs'].values():
+        if old is None:
+            try:
+                delattr(owner, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(owner, name, old)
