@@ -69,7 +69,9 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *map
 // (address bit 4 ^= address bit 7; rows are 32 bytes, the stage base is 1024-byte aligned)
 __device__ __forceinline__ unsigned swz(int L, int half) { return (unsigned)(L * 32 + ((half ^ ((L >> 2) & 1)) << 4)); }
 
-template <int NH, int BW, int MR>
+// NT: number of planes known at compile time (0 = run-time N): the harmonic sums are then fully unrolled and the basis constants
+// become immediate constant-bank operands (no loop control, no uniform loads)
+template <int NH, int BW, int MR, int NT>
 __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ CUtensorMap tmap, PixArgs a, typename BasisSel<NH>::type bs, TmaArgs ta) {
     constexpr int TR = MR + BW - 1;                     // tile rows
     constexpr int HH = BW / 2;                          // window extent before the centre (rows above / columns left)
@@ -79,7 +81,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     extern __shared__ __align__(16) unsigned char smem[];
     const pb_outputs out = a.outs[blockIdx.y];
     const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
-    const int N = a.N, H = a.H, W = a.W;
+    const int N = NT ? NT : a.N, H = a.H, W = a.W;
     const int y0 = blockIdx.x * MR;
     const int tid = threadIdx.x, warp = tid >> 5;
     const unsigned sbase = smem_u32(smem);
@@ -160,8 +162,11 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
         for (int p = 0; p < N; ++p, L += TR) {
             const uint4 w = *reinterpret_cast<const uint4 *>(raw + swz(L, half));
             const unsigned m0 = __vmaxu2(w.x, dark2), m1 = __vmaxu2(w.y, dark2), m2 = __vmaxu2(w.z, dark2), m3 = __vmaxu2(w.w, dark2);
-            acc[0] += m0 & 0xffffu; acc[1] += m0 >> 16; acc[2] += m1 & 0xffffu; acc[3] += m1 >> 16;
-            acc[4] += m2 & 0xffffu; acc[5] += m2 >> 16; acc[6] += m3 & 0xffffu; acc[7] += m3 >> 16;
+            // __dp2a_lo(m, b, c) = c + m.lo16 * b.byte0 + m.hi16 * b.byte1: b = 0x0001 adds the low halfword, b = 0x0100 the high one
+            acc[0] = __dp2a_lo(m0, 0x0001u, acc[0]); acc[1] = __dp2a_lo(m0, 0x0100u, acc[1]);
+            acc[2] = __dp2a_lo(m1, 0x0001u, acc[2]); acc[3] = __dp2a_lo(m1, 0x0100u, acc[3]);
+            acc[4] = __dp2a_lo(m2, 0x0001u, acc[4]); acc[5] = __dp2a_lo(m2, 0x0100u, acc[5]);
+            acc[6] = __dp2a_lo(m3, 0x0001u, acc[6]); acc[7] = __dp2a_lo(m3, 0x0100u, acc[7]);
         }
         uint4 *dst = reinterpret_cast<uint4 *>(Tt + rr * TPB + half * 32);
         dst[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
@@ -281,7 +286,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                     if (cand) {
                         double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
                         const double *fp = pfp;
-#pragma unroll 6
+#pragma unroll(NT ? NT : 6)
                         for (int i = 0; i < N; ++i) {
                             const double f = *fp;
                             fp += PLD;
@@ -369,7 +374,7 @@ size_t plan(const PixArgs &a, TmaArgs &ta) {
     return off;
 }
 
-template <int NH, int BW, int MR>
+template <int NH, int BW, int MR, int NT>
 cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st) {
     constexpr int TR = MR + BW - 1;
     TmaArgs ta;
@@ -390,7 +395,7 @@ cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int 
     if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void *>(a.stack), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    auto kern = k_march_tma<NH, BW, MR>;
+    auto kern = k_march_tma<NH, BW, MR, NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((a.H + MR - 1) / MR, n_stacks);
@@ -411,10 +416,21 @@ inline int rows_for(int N, int H, int n_stacks) {
 
 template <int NH, int BW>
 cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st) {
-    switch (rows_for(a.N, a.H, n_stacks)) {
-    case 16: return launch<NH, BW, 16>(a, bs, n_stacks, st);
-    case 8: return launch<NH, BW, 8>(a, bs, n_stacks, st);
-    default: return launch<NH, BW, 4>(a, bs, n_stacks, st);
+    const int mr = rows_for(a.N, a.H, n_stacks);
+    // the reference's standard 1PF acquisition (18 angles, PP:1926) with the small windows has fully unrolled variants
+    if constexpr (NH == 1 && BW <= 5) {
+        if (a.N == 18) {
+            switch (mr) {
+            case 16: return launch<NH, BW, 16, 18>(a, bs, n_stacks, st);
+            case 8: return launch<NH, BW, 8, 18>(a, bs, n_stacks, st);
+            default: return launch<NH, BW, 4, 18>(a, bs, n_stacks, st);
+            }
+        }
+    }
+    switch (mr) {
+    case 16: return launch<NH, BW, 16, 0>(a, bs, n_stacks, st);
+    case 8: return launch<NH, BW, 8, 0>(a, bs, n_stacks, st);
+    default: return launch<NH, BW, 4, 0>(a, bs, n_stacks, st);
     }
 }
 
