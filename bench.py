@@ -219,6 +219,150 @@ def workload_config(a, ilow):
             'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
 
 
+def pin_rank_cpus(local: int, world: int):
+    """Give each rank of one box its own slice of the CPUs this process may use (the copy engines' staging threads and the Python
+    driver of a rank then stay put). The GPU boxes of this pool are VMs with one visible NUMA node (SCALE_r01 topology: every GPU
+    reports CPU affinity 0-31, NUMA 0, GPU NUMA ID N/A), so there is no per-GPU NUMA node to bind to."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= 2 * world:
+            per = len(cpus) // world
+            os.sched_setaffinity(0, cpus[local * per:(local + 1) * per])
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
+def device_g1_frame(frame, seed: int, dark: int = 480):
+    """Generator G1 (the formulas of polarimetry_b200.synth.stack_1pf) on the device, plane by plane, for frames too
+    large to draw on the host: fills frame [N,H,W] (int16 storage of the uint16 bit pattern)."""
+    import math
+    import torch
+    N, H, W = frame.shape
+    dev = frame.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    x = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
+    y = torch.arange(H, device=dev, dtype=torch.float32)[:, None]
+    rho0 = torch.remainder(180.0 * x / W, 180.0) * (math.pi / 180.0)
+    mod = 0.05 + 0.9 * y / H
+    I0 = 2000.0 + 1500.0 * torch.sin(x / 37.0) * torch.cos(y / 53.0)
+    for k in range(N):
+        lam = I0 * (1.0 + mod * torch.cos(2.0 * (-math.pi * k / N - rho0)))
+        v = torch.poisson(lam.clamp_(min=0.0), generator=g) + float(dark)
+        frame[k] = v.clamp_(0, 65535).to(torch.int32).to(torch.int16)
+        del lam, v
+
+
+def run_timeseries(a):
+    """BASELINE configs[4]: large-field time series, 64 frames of 8192x8192x90 uint16, bin 5x5, per-frame rho/psi histograms.
+    Frames are independent: sharded over the ranks (polarimetry_b200.batch.TimeSeriesAnalyzer), every frame keeps its own
+    histograms, ONE all-reduce of the [n_frames, groups, vars, nbins] buffer per step gives every rank the whole series.
+    Weak scaling: each GPU holds `--frames-per-gpu` resident frames (8 = its share of the 64 at 8 GPUs)."""
+    import torch
+    import torch.distributed as dist
+    from polarimetry_b200 import AnalysisParams, Calibration, Engine
+    from polarimetry_b200.batch import TimeSeriesAnalyzer, shard_range
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    ncpu = pin_rank_cpus(local, world)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+    eng = Engine(local)
+    F, N, Hf = a.frames_per_gpu, 90, a.field
+    n_frames = F * world
+    own = shard_range(n_frames, rank, world)
+    d = np.load(DISK)
+    cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
+    frames = torch.empty((F, N, Hf, Hf), dtype=torch.int16, device=dev)
+    for k, f in enumerate(own):
+        device_g1_frame(frames[k], seed=f)
+    frames = frames.view(torch.uint16)
+    bins = (a.bin, a.bin)
+    ilow = a.ilow
+    if ilow is None:       # G1 threshold from the threshold image of frame 0 (same value on every rank: frame 0 is regenerated locally)
+        f0 = torch.empty((N, Hf, Hf), dtype=torch.int16, device=dev)
+        device_g1_frame(f0, seed=0)
+        ilow = g1_ilow(eng.get_intensity(f0.view(torch.uint16), DARK, bins).cpu().numpy())
+        del f0
+    p = AnalysisParams(method='1PF', dark=DARK, bins=bins, ilow=ilow, out_dtype='float32')
+    ts = TimeSeriesAnalyzer(eng, p, cal)
+    launches0 = eng.launch_count()
+    W3 = max(a.warmup, 3)
+    for _ in range(W3):
+        o = ts.run(frames, n_frames, rank, world, reduce=world > 1)
+    torch.cuda.synchronize()
+    launches_per_step = (eng.launch_count() - launches0) // W3
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record()
+    for s in range(a.steps):
+        o = ts.run(frames, n_frames, rank, world, reduce=world > 1)
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[s].elapsed_time(ev[s + 1]) for s in range(a.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    value = n_frames * Hf * Hf * N * a.steps / (total_ms * 1e-3) / 1e6
+    # checks on the timed outputs: every frame of the series has its histogram (also the other ranks' frames after the reduction),
+    # each frame's rho histogram counts its valid pixels, and the local frames' counts equal their masks
+    hf = o['hist_frames'].cpu().numpy()
+    assert hf.shape[0] == n_frames and all(int(hf[f, 0, 0].sum()) > 0 for f in range(n_frames))
+    for k, f in enumerate(own):
+        assert int(hf[f, 0, 0].sum()) == int(o['mask'][k].sum().item()), f
+    valid_frac = float(o['mask'].float().mean().item())
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = F * (Hf * Hf * N * 2 + Hf * Hf * OUT_BYTES_PER_PIXEL)
+    kern_ms = float(np.median(step_ms))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'kernel': o['plan'], 'algorithmic_bytes_per_launch': alg_bytes, 'note': 'one launch = this rank\'s resident frames; duration = median CUDA-event step time'}
+    # e2e: one frame per call from pinned host memory (12.1 GB in), maps + mask + per-frame histograms back
+    e2e = None
+    if not a.no_e2e:
+        host = frames[:1].view(torch.int16).cpu().pin_memory().view(torch.uint16)
+        hout = {}
+        eng.analyze_host(host, p, cal, out=hout)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ho = eng.analyze_host(host, p, cal, out=hout)
+            _ = int(ho['hist'].sum())
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * Hf * Hf * N * reps / float(te.item()) / 1e6, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': Hf * Hf * N * 2,
+               'd2h_bytes_per_step': Hf * Hf * OUT_BYTES_PER_PIXEL + 2 * 60 * 8, 'stacks_per_step': 1,
+               'api': 'Engine.analyze_host -> pb_analyze_host, one frame per call'}
+    if rank == 0:
+        cfg = {'workload': f'1PF time series (BASELINE configs[4]): {n_frames} frames of {Hf}x{Hf}x{N} uint16 (generator G1 on the device), dark {DARK:.0f}, '
+                           f'bin {a.bin}x{a.bin}, disk-cone LUT, G1 threshold, rho/psi/intensity maps f32 + mask + per-frame rho/psi histograms (60 bins)',
+               'ilow': ilow, 'bin': [a.bin, a.bin], 'l2': 'inputs larger than L2 (no flush needed)', 'precision_mode': 'exact (fp64 replay, bit-exact bins)'}
+        print(json.dumps({'metric': 'Mpixel-angles/s', 'value': value, 'unit': 'Mpx-angles/s', 'n_gpus': world, 'steps': a.steps, 'warmup': W3,
+                          'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+                          'data': 'synthetic', 'config': cfg, 'frames_per_gpu': F, 'frames_total': n_frames, 'valid_pixel_fraction': round(valid_frac, 4),
+                          'plan': o['plan'], 'roofline': roofline, 'cpu_baseline': None, 'e2e': e2e, 'gpu_launches': int(launches_per_step * a.steps),
+                          'collective': 'one all_reduce(SUM) of the [frames, groups, vars, nbins] int64 buffer per step' if world > 1 else None,
+                          'cpus_per_rank': ncpu, 'clocks': clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -231,10 +375,16 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--ilow', type=float, default=None, help='intensity threshold (1pf workloads); default = SURVEY G1 (20th percentile of the '
                                                              'intensity image, ~80 %% of the pixels valid); 0 keeps every pixel')
-    ap.add_argument('--workload', default='1pf', choices=sorted(WORKLOADS), help='1pf = the headline (BASELINE configs[3]); shg / 4polar3d = configs[1] / [2], reported for information')
+    ap.add_argument('--workload', default='1pf', choices=sorted(WORKLOADS) + ['timeseries'],
+                    help='1pf = the headline (BASELINE configs[3]); shg / 4polar3d = configs[1] / [2]; timeseries = configs[4] (use --bin 5)')
+    ap.add_argument('--frames-per-gpu', type=int, default=8, help='timeseries: resident frames per GPU (8 = one GPU\'s share of the 64 frames at 8 GPUs)')
+    ap.add_argument('--field', type=int, default=8192, help='timeseries: frame height = width')
+    ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg')
     a = ap.parse_args()
     if a.impl == 'reference':
         return run_reference_arm(a)
+    if a.workload == 'timeseries':
+        return run_timeseries(a)
 
     import torch
     import torch.distributed as dist
@@ -244,6 +394,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    ncpu = pin_rank_cpus(local, world)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -368,10 +519,39 @@ def main():
     evp[1].record()
     torch.cuda.synchronize()
     h2d_gbs = 3 * host.numel() * 2 / (evp[0].elapsed_time(evp[1]) * 1e-3) / 1e9
+    # ... and the same with every rank of the box copying at the same time (the host side is shared: memory, PCIe root, IOMMU)
+    h2d_all = h2d_gbs
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        evp[0].record()
+        for _ in range(3):
+            dprobe.copy_(host, non_blocking=True)
+        evp[1].record()
+        torch.cuda.synchronize()
+        tl = torch.tensor([evp[0].elapsed_time(evp[1])], dtype=torch.float64, device=dev)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        h2d_all = 3 * host.numel() * 2 / (float(tl.item()) * 1e-3) / 1e9
     del dprobe
+    # batch mode of configs[3] wants the reduced histograms only: the same call without the map D2H
+    hout2 = {}
+    eng.analyze_host(host_u16, p, cal, out=hout2, want_maps=False)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ho = eng.analyze_host(host_u16, p, cal, out=hout2, want_maps=False)
+        _ = int(ho['hist'].sum())
+    th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    e2e_hist = Be * H * W * N * world * e2e_steps / float(th.item()) / 1e6
     e2e = {'value': e2e_val, 'unit': 'Mpx-angles/s', 'h2d_bytes_per_step': Be * H * W * N * 2,
            'd2h_bytes_per_step': Be * (H * W * out_bpp) + 2 * 60 * 8, 'stacks_per_step': Be, 'h2d_pinned_gbs': round(h2d_gbs, 2),
-           'frac_of_h2d_ceiling': round(e2e_val * 1e6 * 2 / 1e9 / h2d_gbs, 3),
+           'h2d_pinned_gbs_per_gpu_all_ranks_copying': round(h2d_all, 2),
+           'frac_of_h2d_ceiling': round(e2e_val / world * 1e6 * 2 / 1e9 / h2d_all, 3),
+           'histograms_only': {'value': e2e_hist, 'd2h_bytes_per_step': 2 * 60 * 8, 'frac_of_h2d_ceiling': round(e2e_hist / world * 1e6 * 2 / 1e9 / h2d_all, 3)},
+           'cpus_per_rank': ncpu,
            'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
 
     # size-independent sanity of the timed outputs: every valid pixel has a rho inside [0, 180] -> one histogram count each

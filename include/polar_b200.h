@@ -141,6 +141,20 @@ int pb_histo(pb_ctx *ctx, const void *values_dev, int is_f64, const uint8_t *sel
 int pb_stats(pb_ctx *ctx, const void *values_dev, const void *rho_dev, int is_f64, const uint8_t *sel_dev, long n, int circular,
              double rotation_fig, int fold90, double *out_host, void *stream);
 
+/* Batch form of the same reductions (ROI statistics of a batch sharded over GPUs; semantic model merge_histos /
+ * return_vecexcel on the concatenated values, PP:2318-2384, PP:2739-2779). Statistic slots v = 0 .. n_vars: the method's primary
+ * variables (Rho first: circular, re-wrapped with params->rotation_fig) and, last, intmap; for every histogram group g
+ * (pb_set_rois) over the pixels of ALL n_stacks maps with the group's ROI bit set and a finite Rho:
+ *   pass 1: acc1[g][v][0..2] += N, sum d (Rho: sum cos 2d), (Rho: sum sin 2d)         acc1: double [n_groups][PB_MAX_VARS+1][4]
+ *   pass 2: acc2[g][v][0..1] += sum delta, sum delta^2                                  acc2: double [n_groups][PB_MAX_VARS+1][2]
+ *           delta = d - mean (Rho: wrapto180(2(d - mean))/2), the means FINALISED ON THE DEVICE from acc1.
+ * The accumulators are plain sums: a batch sharded over several GPUs all-reduces acc1 between the passes and acc2 after
+ * (two messages of a few hundred bytes), then N, mean, std = sqrt(sum delta^2 / N - (sum delta / N)^2) follow on the host.
+ * outs_host: the DEVICE map pointers of each stack as written by pb_analyze (var[], intmap). Zero the accumulators first.
+ * Asynchronous on `stream`; never synchronises. */
+int pb_stats_batch(pb_ctx *ctx, const pb_params *params, int pass, const pb_outputs *outs_host, int n_stacks, const uint32_t *roi_bits_dev,
+                   double *acc1_dev, double *acc2_dev, void *stream);
+
 /* "next" row N2: replaces Stack.compute_dark (PC:266-278): the mean over all angles of the non-zero samples of
  * the size_cell x size_cell cell whose first-angle non-zero mean is smallest. Integer stacks. Synchronises `stream`. */
 int pb_compute_dark(pb_ctx *ctx, const void *stack_dev, int dtype, int N, int H, int W, int size_cell, double *dark_host, void *stream);

@@ -48,6 +48,7 @@ EXPORTS = {
     'pb_fit_maps': (C.c_int, [C.c_void_p, C.POINTER(PbParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb_histo': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'pb_stats': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    'pb_stats_batch': (C.c_int, [C.c_void_p, C.POINTER(PbParams), C.c_int, C.POINTER(PbOutputs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'pb_compute_dark': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     'pb_lut_apply': (C.c_int, [C.c_void_p, C.POINTER(PbParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(PbOutputs), C.c_void_p]),
     'pb_stack_from_hwn': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -373,9 +373,10 @@ class Engine:
                       hist, o['roi_bits'], o['plan'])
 
     def analyze_host(self, stacks_host, p: AnalysisParams, calib: Optional[Calibration] = None, out: Optional[dict] = None,
-                     want_hist: bool = True) -> dict:
+                     want_hist: bool = True, want_maps: bool = True) -> dict:
         """Host buffers in, host buffers out, through `pb_analyze_host` (H2D / kernels / D2H overlapped over two
-        streams). stacks_host: numpy array or pinned CPU tensor [B,N,H,W]. Returns dict of host arrays."""
+        streams). stacks_host: numpy array or pinned CPU tensor [B,N,H,W]. Returns dict of host arrays.
+        want_maps=False: only the reduced histograms come back (batch mode of BASELINE configs[3]: no map D2H)."""
         a = stacks_host if isinstance(stacks_host, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(stacks_host).view(np.int16) if np.asarray(stacks_host).dtype == np.uint16 else np.ascontiguousarray(stacks_host))
         src_dtype = 'uint16' if (not isinstance(stacks_host, torch.Tensor) and np.asarray(stacks_host).dtype == np.uint16) else self._dtype_name(a)
@@ -392,19 +393,21 @@ class Engine:
             pp.flags |= _cabi.FLAG_NO_HIST
         mdt = torch.float64 if p.out_dtype == 'float64' else torch.float32
         o = out if out is not None else {}
-        if 'vars' not in o:
+        if want_maps and 'vars' not in o:
             pin = dict(pin_memory=True)
             o['vars'] = {n: torch.empty((B, H, W), dtype=mdt, **pin) for n in names}
             o['intmap'] = torch.empty((B, H, W), dtype=mdt, **pin)
             o['mask'] = torch.empty((B, H, W), dtype=torch.uint8, **pin)
+        if 'hist' not in o:
             o['hist'] = torch.zeros((1, ng, len(names), p.nbins), dtype=torch.int64)
         o['hist'].zero_()
         outs = (PbOutputs * B)()
         for b in range(B):
-            for k, n in enumerate(names):
-                outs[b].var[k] = o['vars'][n][b].data_ptr()
-            outs[b].intmap = o['intmap'][b].data_ptr()
-            outs[b].mask = o['mask'][b].data_ptr()
+            if want_maps:
+                for k, n in enumerate(names):
+                    outs[b].var[k] = o['vars'][n][b].data_ptr()
+                outs[b].intmap = o['intmap'][b].data_ptr()
+                outs[b].mask = o['mask'][b].data_ptr()
             if want_hist:
                 outs[b].hist = o['hist'][0].data_ptr()
         self._ck(self.lib.pb_analyze_host(self._ctx, C.byref(pp), a.data_ptr(), B, None, None, outs), 'pb_analyze_host')
@@ -701,6 +704,32 @@ class Engine:
         s3 = self.stats(res.intmap, rho, sel, False)
         out['MeanInt'], out['StdInt'] = s3['mean'], s3['std']
         return out
+
+    def batch_stats_accumulate(self, o: dict, p: AnalysisParams, reduce_fn=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The moment sums of return_vecexcel (PP:2739-2779) over EVERY map of the batch `o` (the dict analyze_batch returned):
+        two launches (pb_stats_batch pass 1 / pass 2), nothing synchronises, the means are finalised on the device. `reduce_fn`
+        (e.g. batch.allreduce_sum_) is applied to each accumulator right after its pass: that is the whole exchange of a batch
+        sharded over several GPUs (SURVEY 8e). Returns device tensors acc1 [groups, PB_MAX_VARS+1, 4], acc2 [groups, PB_MAX_VARS+1, 2];
+        batch.finalize_stats turns them into N / mean / std per group and variable."""
+        names = VAR_NAMES[p.method]
+        B, H, W = o['intmap'].shape
+        ng = len(o['roi_indices'])
+        N = o['_keep'][0].shape[1]
+        pp = self._params(p, self._dtype_name(o['_keep'][0]), N, H, W)
+        acc1 = torch.zeros((ng, _cabi.PB_MAX_VARS + 1, 4), dtype=torch.float64, device=self.device)
+        acc2 = torch.zeros((ng, _cabi.PB_MAX_VARS + 1, 2), dtype=torch.float64, device=self.device)
+        outs = (PbOutputs * B)()
+        for b in range(B):
+            for k, n in enumerate(names):
+                outs[b].var[k] = o['vars'][n][b].data_ptr()
+            outs[b].intmap = o['intmap'][b].data_ptr()
+        roi_dev = o['_keep'][1]
+        for npass, acc in ((1, acc1), (2, acc2)):
+            self._ck(self.lib.pb_stats_batch(self._ctx, C.byref(pp), npass, outs, B, _ptr(roi_dev), acc1.data_ptr(), acc2.data_ptr(),
+                                             self._stream()), 'pb_stats_batch')
+            if reduce_fn is not None:
+                reduce_fn(acc)
+        return acc1, acc2
 
     # ---- "next" row N4 (SURVEY 8f): the result writers' boolean-mask gathers, on the device ---------------------------
     def compact(self, values, filter=None, sel=None, roi_bits=None, group_bits: int = 0xffffffff, want: Sequence[str] = ('f16',)) -> dict:

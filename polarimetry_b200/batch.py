@@ -47,6 +47,34 @@ def circular_mean_from_moments(m: torch.Tensor) -> float:
     return float(np.mod(np.degrees(np.arctan2(s / n, c / n)), 360.0) / 2.0)
 
 
+def finalize_stats(acc1, acc2, names: Sequence[str]) -> list:
+    """Accumulators of pb_stats_batch (summed over the ranks) -> per histogram group the numeric columns of return_vecexcel
+    (PP:2739-2779): N, MeanRho (circularmean, PC:55-56), StdRho / MeanDeltaRho (of wrapto180(2(d - mean))/2), Mean / Std of the
+    other variables and of the intensity. acc1 [G, V+1, 4] = N, sum d | sum cos 2d, sum sin 2d; acc2 [G, V+1, 2] = sum delta,
+    sum delta^2 (np.std is the population standard deviation: sqrt(mean(delta^2) - mean(delta)^2) with delta = d - mean)."""
+    a1 = acc1.detach().cpu().numpy() if isinstance(acc1, torch.Tensor) else np.asarray(acc1)
+    a2 = acc2.detach().cpu().numpy() if isinstance(acc2, torch.Tensor) else np.asarray(acc2)
+    rows = []
+    for g in range(a1.shape[0]):
+        n = float(a1[g, 0, 0])
+        row = {'N': int(n)}
+        with np.errstate(invalid='ignore', divide='ignore'):
+            for v, name in enumerate(list(names) + ['Int']):
+                s1, s2 = a1[g, v, 1], a1[g, v, 2]
+                if v == 0:
+                    mean = float(np.mod(np.degrees(np.arctan2(s2 / n, s1 / n)), 360.0) / 2.0) if n else float('nan')
+                else:
+                    mean = float(s1 / n) if n else float('nan')
+                md = a2[g, v, 0] / n if n else float('nan')
+                var = a2[g, v, 1] / n - md * md if n else float('nan')
+                std = float(np.sqrt(max(var, 0.0))) if n else float('nan')
+                row['Mean' + name], row['Std' + name] = mean, std
+                if v == 0:
+                    row['MeanDeltaRho'] = float(md)
+        rows.append(row)
+    return rows
+
+
 class BatchAnalyzer:
     """Analyse this rank's shard of a batch and reduce the histograms over all ranks."""
 
@@ -61,6 +89,14 @@ class BatchAnalyzer:
         if reduce:
             allreduce_sum_(o['hist'], self.group)
         return o
+
+    def stats(self, o: dict, reduce: bool = True) -> list:
+        """ROI statistics of the WHOLE batch (all ranks' stacks, as if their values were concatenated: the reference's merge
+        semantics): moment sums on the device, one small all-reduce after each of the two passes, finalised on the host."""
+        from .api import VAR_NAMES
+        fn = (lambda t: allreduce_sum_(t, self.group)) if reduce else None
+        acc1, acc2 = self.engine.batch_stats_accumulate(o, self.params, fn)
+        return finalize_stats(acc1, acc2, VAR_NAMES[self.params.method])
 
 
 def place_frames(hist_local: torch.Tensor, own: range, n_frames: int) -> torch.Tensor:
@@ -80,13 +116,16 @@ class TimeSeriesAnalyzer:
 
     def __init__(self, engine, params, calib=None, rois: Optional[Sequence[dict]] = None, per_roi: bool = False, group=None):
         self.engine, self.params, self.calib, self.rois, self.per_roi, self.group = engine, params, calib, rois, per_roi, group
+        self._out = {}          # output maps are allocated once and reused by every call on frames of the same shape
 
     def run(self, frames_local, n_frames: int, rank: int, world: int, reduce: bool = True) -> dict:
         """frames_local: this rank's frames [len(shard_range(n_frames, rank, world)), N, H, W] (device tensor). Returns the engine's
         output dict (maps of the local frames) with o['hist_frames']: int64 [n_frames, n_groups, n_vars, nbins]."""
         own = shard_range(n_frames, rank, world)
+        if self._out and tuple(self._out['mask'].shape) != (frames_local.shape[0],) + tuple(frames_local.shape[-2:]):
+            self._out = {}
         o = self.engine.analyze_batch(frames_local, self.params, self.calib, self.rois, self.per_roi, want_intensity=False,
-                                      hist_per_stack=True)
+                                      hist_per_stack=True, out=self._out)
         full = place_frames(o['hist'], own, n_frames)
         if reduce:
             allreduce_sum_(full, self.group)

@@ -34,6 +34,8 @@ cudaError_t pb_launch_dark_cells(const void *plane0, int dtype, int W, int ny, i
                                  cudaStream_t st);
 cudaError_t pb_launch_dark_cell_all(const void *stack, int dtype, long long P, int W, int N, int y0, int x0, int cell,
                                     unsigned long long *out, cudaStream_t st);
+cudaError_t pb_launch_stats_batch(int pass, const pb_outputs *outs_dev, int n_stacks, const uint32_t *roi_bits, long long P, int n_vars, int f64,
+                                  double rot_fig, const uint32_t *group_bits, int n_groups, double *acc1, double *acc2, cudaStream_t st);
 bool pb_march_supported(const pb_params *p);
 cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches);
 
@@ -589,6 +591,28 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     if (var < 0) var = 0;
     out_host[0] = cnt; out_host[1] = mean; out_host[2] = sqrt(var); out_host[3] = md; out_host[4] = circ ? NAN : acc[1];
     return ws_release(ctx, st);
+}
+
+int pb_stats_batch(pb_ctx *ctx, const pb_params *p, int pass, const pb_outputs *outs_host, int n_stacks, const uint32_t *roi_bits,
+                   double *acc1_dev, double *acc2_dev, void *stream) {
+    if (!ctx || !p || !outs_host || !acc1_dev || !acc2_dev || n_stacks < 1 || (pass != 1 && pass != 2))
+        return fail(ctx, PB_ERR_ARG, "pb_stats_batch: bad argument");
+    const int nv = method_nvars(p->method);
+    if (!nv) return fail(ctx, PB_ERR_ARG, "pb_stats_batch: unknown method");
+    for (int s = 0; s < n_stacks; ++s) {
+        if (!outs_host[s].intmap) return fail(ctx, PB_ERR_ARG, "pb_stats_batch: every stack needs its variable maps and intmap");
+        for (int v = 0; v < nv; ++v)
+            if (!outs_host[s].var[v]) return fail(ctx, PB_ERR_ARG, "pb_stats_batch: every stack needs its variable maps and intmap");
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const pb_outputs *od;
+    int rc;
+    if ((rc = push_outs(ctx, outs_host, n_stacks, st, &od))) return rc;
+    CK(pb_launch_stats_batch(pass, od, n_stacks, roi_bits, (long long)p->H * p->W, nv, (p->flags & PB_FLAG_OUT_F64) ? 1 : 0, p->rotation_fig,
+                             ctx->group_bits, ctx->n_groups, acc1_dev, acc2_dev, st));
+    ctx->launches++;
+    return PB_OK;
 }
 
 int pb_stack_from_hwn(pb_ctx *ctx, const void *stack_hwn, int dtype, int N, int H, int W, void *stack_nhw, void *stream) {

@@ -149,24 +149,38 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     };
     // ---- T tile of tile u: per tile position the sum over the planes of max(v, dark) (PC:261 up to the constant N*dark)
     unsigned char *const Tt = smem + ta.off_T;
+    // The swizzle bit of tile row L = p*TR + rr is periodic in the plane p with period 8 (L grows by 8*TR = a multiple of 8 rows),
+    // so a thread needs 8 byte offsets for all its planes; the loads then take immediate plane offsets.
     auto t_phase = [&](int u, int item) {
         if (item >= TR * 2) return;
         const unsigned char *raw = raw0 + (u & 1) * stage_bytes;
         const int rr = item >> 1, half = item & 1;
         const unsigned dark2 = (unsigned)ta.idark * 0x10001u;
+        unsigned offk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) offk[k] = swz(k * TR + rr, half);
         unsigned acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = 0u;
-        int L = rr;
-#pragma unroll 2
-        for (int p = 0; p < N; ++p, L += TR) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(raw + swz(L, half));
+        auto add_plane = [&](const uint4 w) {
             const unsigned m0 = __vmaxu2(w.x, dark2), m1 = __vmaxu2(w.y, dark2), m2 = __vmaxu2(w.z, dark2), m3 = __vmaxu2(w.w, dark2);
             // __dp2a_lo(m, b, c) = c + m.lo16 * b.byte0 + m.hi16 * b.byte1: b = 0x0001 adds the low halfword, b = 0x0100 the high one
             acc[0] = __dp2a_lo(m0, 0x0001u, acc[0]); acc[1] = __dp2a_lo(m0, 0x0100u, acc[1]);
             acc[2] = __dp2a_lo(m1, 0x0001u, acc[2]); acc[3] = __dp2a_lo(m1, 0x0100u, acc[3]);
             acc[4] = __dp2a_lo(m2, 0x0001u, acc[4]); acc[5] = __dp2a_lo(m2, 0x0100u, acc[5]);
             acc[6] = __dp2a_lo(m3, 0x0001u, acc[6]); acc[7] = __dp2a_lo(m3, 0x0100u, acc[7]);
+        };
+        int p = 0;
+        for (; p + 8 <= N; p += 8) {
+            const unsigned char *base = raw + p * (TR * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) add_plane(*reinterpret_cast<const uint4 *>(base + offk[k]));
+        }
+        {
+            const unsigned char *base = raw + p * (TR * 32);
+#pragma unroll
+            for (int k = 0; k < 7; ++k)
+                if (p + k < N) add_plane(*reinterpret_cast<const uint4 *>(base + offk[k]));
         }
         uint4 *dst = reinterpret_cast<uint4 *>(Tt + rr * TPB + half * 32);
         dst[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
@@ -228,8 +242,8 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                         for (int dy = 0; dy < BW; ++dy) {
                             const unsigned word = k == 0 ? w[dy].x : (k == 1 ? w[dy].y : (k == 2 ? w[dy].z : w[dy].w));
                             const unsigned m = __vmaxu2(word, sub2);
-                            lo += m & 0xffffu;
-                            hi += m >> 16;
+                            lo = __dp2a_lo(m, 0x0001u, lo);       // lo += m & 0xffff, hi += m >> 16: one instruction each
+                            hi = __dp2a_lo(m, 0x0100u, hi);
                         }
                         f[2 * k] = advance(lo, ta.magic, half * 8 + 2 * k);
                         f[2 * k + 1] = advance(hi, ta.magic, half * 8 + 2 * k + 1);

@@ -93,6 +93,96 @@ __global__ void __launch_bounds__(256) k_stats2(const T *vals, const T *rho, con
     if (threadIdx.x == 0) { atomicAdd(acc + 3, s1); atomicAdd(acc + 4, s2); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Batch statistics (return_vecexcel, PP:2739-2779, over every map of a batch): one launch per pass for all stacks,
+// groups and variables, accumulators in device memory, means finalised on the device -> no host round trip between the passes,
+// and the accumulators are plain sums, so a sharded batch needs one small all-reduce per pass.
+struct StatsBatchArgs {
+    const pb_outputs *outs;      // device array [n_stacks]
+    const uint32_t *roi_bits;    // [P] or NULL
+    long long P;
+    int n_vars;                  // primary variables (Rho first); statistic slot n_vars is intmap
+    int f64;
+    double rot_fig;
+    uint32_t group_bits[PB_MAX_ROIS];
+};
+constexpr int SB_SLOTS = PB_MAX_VARS + 1;
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(256) k_stats_batch(StatsBatchArgs a, double *__restrict__ acc1, double *__restrict__ acc2) {
+    __shared__ double sh[8];
+    const int g = blockIdx.z;
+    const pb_outputs o = a.outs[blockIdx.y];
+    const uint32_t gb = a.group_bits[g];
+    const T *maps[SB_SLOTS];
+#pragma unroll
+    for (int v = 0; v < SB_SLOTS; ++v) maps[v] = nullptr;
+#pragma unroll
+    for (int v = 0; v < PB_MAX_VARS; ++v)
+        if (v < a.n_vars) maps[v] = reinterpret_cast<const T *>(o.var[v]);
+    const T *im = reinterpret_cast<const T *>(o.intmap);
+    double mean[SB_SLOTS];
+    if (PASS == 2) {
+        // the means of pass 1 (already summed over the ranks by the caller, if any): circularmean (PC:55-56) for Rho
+#pragma unroll
+        for (int v = 0; v < SB_SLOTS; ++v) {
+            const double *q = acc1 + ((size_t)g * SB_SLOTS + v) * 4;
+            const double n = q[0];
+            if (v == 0) {
+                double ang = atan2(q[2] / n, q[1] / n) * (180.0 / 3.141592653589793238462643383279502884);
+                ang = fmod(ang, 360.0);
+                if (ang < 0) ang += 360.0;
+                mean[v] = ang / 2.0;
+            } else {
+                mean[v] = q[1] / n;
+            }
+        }
+    }
+    double cnt = 0.0, s1[SB_SLOTS], s2[SB_SLOTS];
+#pragma unroll
+    for (int v = 0; v < SB_SLOTS; ++v) s1[v] = s2[v] = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += (long long)gridDim.x * blockDim.x) {
+        const double rho = (double)maps[0][p];
+        if (!pb_finite(rho)) continue;                                            // keep = roi & isfinite(Rho), PP:2742-2743
+        if (a.roi_bits && !(__ldg(a.roi_bits + p) & gb)) continue;
+        cnt += 1.0;
+        const double d = pb_pymod(2.0 * (rho + a.rot_fig), 360.0) / 2.0;         // PP:2744
+        if (PASS == 1) {
+            double sn, cs;
+            sincos(2.0 * d * D2R, &sn, &cs);
+            s1[0] += cs; s2[0] += sn;
+        } else {
+            const double dl = remainder(2.0 * (d - mean[0]), 360.0) / 2.0;       // wrapto180(2(d - mean))/2, PC:73-74
+            s1[0] += dl; s2[0] += dl * dl;
+        }
+#pragma unroll
+        for (int v = 1; v < SB_SLOTS; ++v) {
+            const T *m = v < PB_MAX_VARS ? maps[v] : nullptr;
+            if (v == a.n_vars) m = im;
+            if (v > a.n_vars || !m) continue;
+            const double x = (double)m[p];
+            if (PASS == 1) s1[v] += x;
+            else { const double dl = x - mean[v]; s1[v] += dl; s2[v] += dl * dl; }
+        }
+    }
+    cnt = block_sum(cnt, sh);
+#pragma unroll
+    for (int v = 0; v < SB_SLOTS; ++v) {
+        if (v > a.n_vars) continue;
+        const double r1 = block_sum(s1[v], sh), r2 = block_sum(s2[v], sh);
+        if (threadIdx.x == 0) {
+            if (PASS == 1) {
+                double *q = acc1 + ((size_t)g * SB_SLOTS + v) * 4;
+                atomicAdd(q + 0, cnt); atomicAdd(q + 1, r1); atomicAdd(q + 2, r2);
+            } else {
+                double *q = acc2 + ((size_t)g * SB_SLOTS + v) * 2;
+                atomicAdd(q + 0, r1); atomicAdd(q + 1, r2);
+            }
+        }
+    }
+}
+
 template <int NH>
 __global__ void __launch_bounds__(256) k_fit_maps(const double *__restrict__ f, const uint8_t *__restrict__ mask, long long P, int N,
                                                   typename BasisSel<NH>::type bs, double *__restrict__ fit, double *__restrict__ chi2o) {
@@ -206,6 +296,24 @@ cudaError_t pb_launch_fit_maps(const double *f, const uint8_t *mask, long long P
         k_fit_maps<1><<<blocks, 256, 0, st>>>(f, mask, P, N, b1, fit, chi2);
     } else {
         k_fit_maps<2><<<blocks, 256, 0, st>>>(f, mask, P, N, bs, fit, chi2);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pb_launch_stats_batch(int pass, const pb_outputs *outs_dev, int n_stacks, const uint32_t *roi_bits, long long P, int n_vars, int f64,
+                                  double rot_fig, const uint32_t *group_bits, int n_groups, double *acc1, double *acc2, cudaStream_t st) {
+    StatsBatchArgs a;
+    a.outs = outs_dev; a.roi_bits = roi_bits; a.P = P; a.n_vars = n_vars; a.f64 = f64; a.rot_fig = rot_fig;
+    for (int g = 0; g < PB_MAX_ROIS; ++g) a.group_bits[g] = g < n_groups ? group_bits[g] : 0u;
+    int bx = (int)((P + 255) / 256 < 148LL * 4 ? (P + 255) / 256 : 148LL * 4);
+    if (bx < 1) bx = 1;
+    dim3 grid(bx, n_stacks, n_groups);
+    if (f64) {
+        if (pass == 1) k_stats_batch<double, 1><<<grid, 256, 0, st>>>(a, acc1, acc2);
+        else k_stats_batch<double, 2><<<grid, 256, 0, st>>>(a, acc1, acc2);
+    } else {
+        if (pass == 1) k_stats_batch<float, 1><<<grid, 256, 0, st>>>(a, acc1, acc2);
+        else k_stats_batch<float, 2><<<grid, 256, 0, st>>>(a, acc1, acc2);
     }
     return cudaGetLastError();
 }

@@ -457,3 +457,70 @@ def test_full_size_time_series_frame_properties():
     r = mod.run(8192, 90, 5, reps=1)
     assert r['plan'] == 'fused_march' and r['all_ok'], r['checks']
     assert 0.2 < r['valid_pixel_fraction'] < 0.6
+
+
+@pytest.mark.parametrize('method', ['1PF', 'SHG'])
+def test_batch_statistics_over_two_shards(eng, method):
+    """ROI statistics of a batch split into two shards (what two ranks hold) through pb_stats_batch -- moment sums on the
+    device, the two accumulators summed between / after the passes as the all-reduce does -- equal the reference's statistics on the
+    concatenated values of all stacks at its 3 decimals (and to 1e-9), per ROI group."""
+    from polarimetry_b200 import batch, synth
+    from polarimetry_b200.api import VAR_NAMES
+    B, H, W = 6, 48, 64
+    c = util.CASE_BY_NAME['1pf_rois']
+    if method == '1PF':
+        stacks = np.stack([synth.stack_1pf(H, W, 18, seed=300 + b) for b in range(B)])
+        p = AnalysisParams(method='1PF', dark=480.0, bins=(3, 3), rotation=(0.0, 25.0, 0.0))
+        op = rs.Params(method='1PF', dark=480.0, bins=(3, 3), rotation=(0.0, 25.0, 0.0))
+        cal, ocal = calib_for(util.CASE_BY_NAME['1pf_bin1x1']), util.load_disk(cases.DISK_NODIST)
+    else:
+        stacks = np.stack([synth.stack_4harm(H, W, 36, seed=300 + b) for b in range(B)])
+        p, op, cal, ocal = AnalysisParams(method='SHG'), rs.Params(method='SHG'), None, None
+    rois = c['rois']
+    shards = [stacks[:4], stacks[4:]]
+    outs = [eng.analyze_batch(s, p, cal, rois, True, want_hist=False) for s in shards]
+    keep = []                                                    # what the all-reduce would carry
+
+    def fake_allreduce(t):
+        keep.append(t)
+
+    accs = [eng.batch_stats_accumulate(o, p, None) for o in outs]          # single-shard sanity: runs both passes
+    assert all(torch.isfinite(a1[:, 0, 0]).all() for a1, _ in accs)
+    # two-rank emulation: pass 1 on both shards, sum, pass 2 on both shards with the summed acc1, sum
+    import ctypes as C
+    from polarimetry_b200._cabi import PbOutputs
+    names = VAR_NAMES[method]
+
+    def run_pass(o, npass, acc1, acc2):
+        Bs = o['intmap'].shape[0]
+        po = (PbOutputs * Bs)()
+        for b in range(Bs):
+            for k, n in enumerate(names):
+                po[b].var[k] = o['vars'][n][b].data_ptr()
+            po[b].intmap = o['intmap'][b].data_ptr()
+        pp = eng._params(p, 'uint16', stacks.shape[1], H, W)
+        eng._ck(eng.lib.pb_stats_batch(eng._ctx, C.byref(pp), npass, po, Bs, o['_keep'][1].data_ptr(), acc1.data_ptr(), acc2.data_ptr(),
+                                       eng._stream()), 'pb_stats_batch')
+
+    ng = len(outs[0]['roi_indices'])
+    a1 = [torch.zeros((ng, 5, 4), dtype=torch.float64, device=eng.device) for _ in shards]
+    a2 = [torch.zeros((ng, 5, 2), dtype=torch.float64, device=eng.device) for _ in shards]
+    for o, x1, x2 in zip(outs, a1, a2):
+        run_pass(o, 1, x1, x2)
+    tot1 = a1[0] + a1[1]
+    for o, x2 in zip(outs, a2):
+        run_pass(o, 2, tot1, x2)
+    rows = batch.finalize_stats(tot1, a2[0] + a2[1], names)
+    # reference: the statistics of the concatenated values (every stack analysed by the oracle, maps stacked along the rows)
+    refs = [rs.analyze_stack(s, op, ocal, rois, True, want_stats=False) for s in stacks]
+    cat = {'vars': {n: np.concatenate([r['vars'][n] for r in refs], axis=0) for n in names},
+           'intmap': np.concatenate([r['intmap'] for r in refs], axis=0)}
+    roi_map = np.concatenate([refs[0]['roi_map']] * B, axis=1)
+    for g, idx in enumerate(outs[0]['roi_indices']):
+        want = rs.vecstats(cat, roi_map, op, idx)
+        assert rows[g]['N'] == want['N'] and want['N'] > 50
+        for k, v in want.items():
+            if k == 'N':
+                continue
+            assert rs.fmt3(float(rows[g][k])) == rs.fmt3(float(v)), (g, k, rows[g][k], v)
+            assert abs(rows[g][k] - v) <= 1e-9 * max(1.0, abs(v)), (g, k)

@@ -105,3 +105,55 @@ def test_c_contract_rescale_matches_reference():
         assert np.array_equal(contract.rescale(g[f'{kind}__in']), g[f'{kind}__out'])
     a = g['f32__in'].astype(np.float64) * 1.000001
     assert np.array_equal(contract.rescale(a), rs.define_stack_values(a))
+
+
+@pytest.mark.gpu
+def test_folder_pipeline_equals_file_by_file(tmp_path):
+    """Folder mode with overlap (FolderAnalyzer): a mix of uint16 and float32 multi-page TIFFs of two sizes; every file's maps and
+    histograms equal the serial define_stack -> set_dark -> analyze of the same file, and (uint16 files) the oracle."""
+    import cv2
+    import torch
+    from polarimetry_b200 import AnalysisParams, Calibration, Engine, synth
+    from polarimetry_b200.ingest import FolderAnalyzer
+    from oracle import cases
+    eng = Engine(0)
+    o = util.load_disk(cases.DISK_NODIST)
+    cal = Calibration(o.rho_table, o.psi_table, o.grid.size)
+    files, stacks = [], []
+    for k in range(7):
+        h, w = ((64, 96), (48, 80))[k % 2]
+        v = synth.stack_1pf(h, w, 18, seed=40 + k)
+        v[:, :22, :22] = np.minimum(v[:, :22, :22], 520 + k)            # a dark corner: compute_dark finds it
+        a = v.astype(np.float32) * 0.37 + 3.0 if k == 3 else v           # one float TIFF (rescaled on the device, PP:1929-1930)
+        f = tmp_path / f'stack_{k}.tif'
+        assert cv2.imwritemulti(str(f), list(a))
+        files.append(f)
+        stacks.append(a)
+    p = AnalysisParams(method='1PF', bins=(3, 3), ilow=30000.0)
+    got = {}
+
+    def keep(i, f, res, dark):
+        got[i] = (dark, {v.name: v.values.cpu().numpy() for v in res.vars}, res.mask.cpu().numpy().astype(bool), dict(res.hist))
+
+    fa = FolderAnalyzer(eng, p, cal, slots=3, decode_threads=2)
+    recs = fa.run(files, keep)
+    assert [r['file'] for r in recs] == [str(f) for f in files] and len(fa.timeline) == len(files)
+    rep = fa.overlap_report()
+    assert rep['files'] == 7 and rep['wall_ms'] > 0
+    for k, f in enumerate(files):
+        st = eng.define_stack(f)
+        dark = float('{:.0f}'.format(st['dark']))
+        assert got[k][0] == dark
+        res = eng.analyze(st['values'], AnalysisParams(method='1PF', bins=(3, 3), ilow=30000.0, dark=dark), cal)
+        for v in res.vars:
+            assert util.eq(got[k][1][v.name], v.values.cpu().numpy()), (k, v.name)
+        assert util.eq(got[k][2], res.mask.cpu().numpy().astype(bool))
+        for key, h in res.hist.items():
+            assert util.eq(got[k][3][key], h)
+        vals = rs.define_stack_values(stacks[k])
+        assert dark == float('{:.0f}'.format(rs.compute_dark(vals)))
+        ref = rs.analyze_stack(vals, rs.Params(method='1PF', bins=(3, 3), ilow=30000.0, dark=dark), o, want_stats=False)
+        for name, arr in ref['vars'].items():
+            assert util.eq(got[k][1][name], arr), (k, name)
+        assert util.eq(got[k][2], ref['mask'])
+    eng.close()
