@@ -380,6 +380,9 @@ def main():
     ap.add_argument('--frames-per-gpu', type=int, default=8, help='timeseries: resident frames per GPU (8 = one GPU\'s share of the 64 frames at 8 GPUs)')
     ap.add_argument('--field', type=int, default=8192, help='timeseries: frame height = width')
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg')
+    ap.add_argument('--rho-span', type=float, default=180.0, help='1pf: orientation range of the synthetic sample in degrees (180 = generator G1; '
+                                                                  '6 = an aligned fibre whose rho falls into 2-3 histogram bins: contention variant)')
+    ap.add_argument('--hist-match', action='store_true', help='warp-aggregate the histogram updates with a match on the bin (PB_FLAG_HIST_MATCH)')
     a = ap.parse_args()
     if a.impl == 'reference':
         return run_reference_arm(a)
@@ -405,11 +408,11 @@ def main():
     d = np.load(DISK)
     if method == '1PF':
         cal = Calibration(d['RoTest'], d['PsiTest'], int(d['NbMapValues']))
-        gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed)
+        gen = lambda seed: synth.stack_1pf(H, W, N, seed=seed, rho_lo=40.0 if a.rho_span < 180.0 else 0.0, rho_span=a.rho_span)
         ilow = a.ilow
         if ilow is None:      # G1 threshold from the threshold image of the seed-0 stack, through the product's own seam
             ilow = g1_ilow(eng.get_intensity(gen(0), DARK, (a.bin, a.bin)).cpu().numpy())
-        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32')
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32', hist_match=a.hist_match)
     elif method == 'SHG':
         cal = None
         ilow = 40000.0

@@ -52,6 +52,10 @@ typedef enum pb_dtype { PB_U8 = 0, PB_U16 = 1, PB_F32 = 2, PB_F64 = 3 } pb_dtype
                                     PP:2989), intmap = a0 (PP:2987) and mask = the mask of PP:3000 -- the disk-independent part of the
                                     analysis, input of pb_lut_apply. Implies double maps and no histograms. */
 
+#define PB_FLAG_HIST_MATCH   32u /* warp-aggregate the shared-memory histogram updates with a match on (variable, bin) before the
+                                    atomic: one atomic per distinct bin of a warp instead of one per lane (aligned samples whose
+                                    rho falls into two or three bins); the default leaves the aggregation to the atomic unit */
+
 typedef struct pb_ctx pb_ctx;
 
 /* The settings analyze_stack pulls from the GUI at PP:2950-2968 (SURVEY.md section 5 "Config / flags"). */
@@ -93,6 +97,11 @@ const char *pb_last_error(const pb_ctx *ctx);   /* ctx may be NULL: last creatio
 /* ---- calibration / constants (HOST pointers, copied; synchronous) ------------------------------ */
 /* replaces Calibration.define_disk (PC:460-464): RoTest/PsiTest [n,n] row-major, grid = linspace(-1,1,n) */
 int pb_set_diskcone(pb_ctx *ctx, const double *rho_table_host, const double *psi_table_host, int n, const double *grid_host);
+/* several disk cones resident at once (the 1PF calibration sweep loops over every file of the diskcones folder, PP:850-913):
+ * rho / psi tables [n_disks][n,n] back to back on the host, one common grid. Disk 0 becomes the current one; pb_select_diskcone
+ * switches the table used by the following pb_analyze / pb_lut_apply calls without any copy, allocation or synchronisation. */
+int pb_set_diskcones(pb_ctx *ctx, int n_disks, const double *rho_tables_host, const double *psi_tables_host, int n, const double *grid_host);
+int pb_select_diskcone(pb_ctx *ctx, int disk);
 /* replaces Calibration.invKmat (PC:450-451): pinv(K) row-major [rows,4], rows = 3 (2D) | 4 (3D) */
 int pb_set_invk(pb_ctx *ctx, const double *invk_host, int rows);
 /* harmonic basis computed on the host by NumPy exactly as PP:2983-2986 / PP:2993 (cos/sin of 2a and 4a) */
@@ -150,10 +159,12 @@ int pb_stats(pb_ctx *ctx, const void *values_dev, const void *rho_dev, int is_f6
  *           delta = d - mean (Rho: wrapto180(2(d - mean))/2), the means FINALISED ON THE DEVICE from acc1.
  * The accumulators are plain sums: a batch sharded over several GPUs all-reduces acc1 between the passes and acc2 after
  * (two messages of a few hundred bytes), then N, mean, std = sqrt(sum delta^2 / N - (sum delta / N)^2) follow on the host.
+ * per_stack != 0: one accumulator set per stack (acc1 [n_stacks][n_groups][..], acc2 likewise) instead of one for the batch
+ * (the calibration sweep wants one statistics row per stack, PP:883-898).
  * outs_host: the DEVICE map pointers of each stack as written by pb_analyze (var[], intmap). Zero the accumulators first.
  * Asynchronous on `stream`; never synchronises. */
-int pb_stats_batch(pb_ctx *ctx, const pb_params *params, int pass, const pb_outputs *outs_host, int n_stacks, const uint32_t *roi_bits_dev,
-                   double *acc1_dev, double *acc2_dev, void *stream);
+int pb_stats_batch(pb_ctx *ctx, const pb_params *params, int pass, int per_stack, const pb_outputs *outs_host, int n_stacks,
+                   const uint32_t *roi_bits_dev, double *acc1_dev, double *acc2_dev, void *stream);
 
 /* "next" row N2: replaces Stack.compute_dark (PC:266-278): the mean over all angles of the non-zero samples of
  * the size_cell x size_cell cell whose first-angle non-zero mean is smallest. Integer stacks. Synchronises `stream`. */

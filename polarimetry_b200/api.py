@@ -48,6 +48,7 @@ class AnalysisParams:
     ranges: Dict[str, Tuple[float, float]] = _field(default_factory=lambda: dict(DEFAULT_RANGES))
     out_dtype: str = 'float64'              # 'float64' (bit-comparable maps) or 'float32' (throughput mode)
     exact_chi2: bool = False                # disable the certified chi2 screening
+    hist_match: bool = False                # warp-aggregate histogram updates with a match on the bin (aligned samples)
     force_unfused: bool = False             # run the separate kernels instead of the fused one
 
 
@@ -201,12 +202,33 @@ class Engine:
             self._ck(self.lib.pb_set_basis(self._ctx, N, _ptr(c2), _ptr(s2), _ptr(c4), _ptr(s4)), 'pb_set_basis')
             self._key_basis = key
 
+    def set_diskcones(self, calibs: Sequence[Calibration]) -> None:
+        """Upload several disk cones at once (pb_set_diskcones): they stay resident and `_set_calib` merely selects among them --
+        no copy, allocation or synchronisation when the calibration sweep (PP:850-913) moves to its next disk."""
+        calibs = list(calibs)
+        if not calibs or any(c.rho_table is None for c in calibs):
+            raise ValueError('set_diskcones: disk-cone Calibrations required')
+        n = calibs[0].grid.size
+        if any(c.grid.size != n or not np.array_equal(c.grid, calibs[0].grid) for c in calibs):
+            raise ValueError('set_diskcones: the disk cones must share one grid (NbMapValues)')
+        rho = np.ascontiguousarray(np.stack([c.rho_table for c in calibs]))
+        psi = np.ascontiguousarray(np.stack([c.psi_table for c in calibs]))
+        self._key_calib, self._resident = None, {}
+        self._ck(self.lib.pb_set_diskcones(self._ctx, len(calibs), _ptr(rho), _ptr(psi), n, _ptr(calibs[0].grid)), 'pb_set_diskcones')
+        self._resident = {c.uid: k for k, c in enumerate(calibs)}
+        self._key_calib = ('disk', calibs[0].uid)
+
     def _set_calib(self, p: AnalysisParams, calib: Optional[Calibration]):
         if p.method == '1PF':
             if calib is None or calib.rho_table is None:
                 raise ValueError('1PF needs a disk-cone Calibration')
             key = ('disk', calib.uid)
+            if key != self._key_calib and calib.uid in getattr(self, '_resident', {}):
+                self._key_calib = None
+                self._ck(self.lib.pb_select_diskcone(self._ctx, self._resident[calib.uid]), 'pb_select_diskcone')
+                self._key_calib = key
             if key != self._key_calib:
+                self._resident = {}
                 n = calib.grid.size
                 self._key_calib = None           # a failed upload must not look cached
                 self._ck(self.lib.pb_set_diskcone(self._ctx, _ptr(calib.rho_table), _ptr(calib.psi_table), n, _ptr(calib.grid)), 'pb_set_diskcone')
@@ -248,6 +270,8 @@ class Engine:
             flags |= _cabi.FLAG_EXACT_CHI2
         if p.force_unfused:
             flags |= _cabi.FLAG_FORCE_UNFUSED
+        if p.hist_match:
+            flags |= _cabi.FLAG_HIST_MATCH
         return PbParams(_cabi.METHODS[p.method], _cabi.DTYPES[dtype], N, H, W, int(p.bins[0]), int(p.bins[1]), flags,
                         float(p.dark), float(p.removed_intensity), float(p.rotation[0]), float(p.rotation[1]),
                         float(p.rotation[2]), float(p.chi2threshold), float(p.ilow))
@@ -567,8 +591,34 @@ class Engine:
         dev_stacks = [self._to_device(s) for s in stacks]
         sel_rois = [r for r in (rois or []) if r.get('select')] if per_roi else []
         targets = [(r['indx'], g) for g, r in enumerate(sel_rois)] or [(None, 0)]
-        projs = [self.project(st, p, rois, per_roi, base_mask) for st in dev_stacks] if project_once else None
         rows = []
+        same_shape = len({tuple(st.shape) for st in dev_stacks}) == 1 and len({st.dtype for st in dev_stacks}) == 1
+        if project_once and same_shape:
+            # the batched form: ONE projection launch for all stacks, the disk cones resident on the device, and per disk one
+            # lut_apply launch + two statistics launches (per-stack accumulators); nothing synchronises until the rows are read
+            from .batch import finalize_stats
+            batch = torch.stack(dev_stacks) if len(dev_stacks) > 1 else dev_stacks[0][None]
+            proj = self.project(batch, p, rois, per_roi, base_mask)
+            S, ng, D = batch.shape[0], len(proj['roi_indices']), len(disks)
+            if any(c.uid not in getattr(self, '_resident', {}) for c in disks):
+                self.set_diskcones(disks)
+            acc1 = torch.zeros((D, S, ng, _cabi.PB_MAX_VARS + 1, 4), dtype=torch.float64, device=self.device)
+            acc2 = torch.zeros((D, S, ng, _cabi.PB_MAX_VARS + 1, 2), dtype=torch.float64, device=self.device)
+            out = {}
+            for d, cal in enumerate(disks):
+                o = self.lut_apply(proj, p, cal, want_hist=False, out=out)
+                o['_keep'] = proj['_keep']
+                self.batch_stats_accumulate(o, p, None, per_stack=True, acc=(acc1[d], acc2[d]))
+            a1, a2 = acc1.cpu().numpy(), acc2.cpu().numpy()
+            for d, cal in enumerate(disks):
+                for k in range(S):
+                    fin = finalize_stats(a1[d, k], a2[d, k], VAR_NAMES['1PF'])
+                    for idx, g in targets:
+                        row = dict(fin[g])
+                        row.update(disk=cal.name or d, stack=k, roi=idx if idx is not None else 1)
+                        rows.append(row)
+            return rows
+        projs = [self.project(st, p, rois, per_roi, base_mask) for st in dev_stacks] if project_once else None
         for d, cal in enumerate(disks):
             for k, st in enumerate(dev_stacks):
                 if project_once:
@@ -705,30 +755,36 @@ class Engine:
         out['MeanInt'], out['StdInt'] = s3['mean'], s3['std']
         return out
 
-    def batch_stats_accumulate(self, o: dict, p: AnalysisParams, reduce_fn=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def batch_stats_accumulate(self, o: dict, p: AnalysisParams, reduce_fn=None, per_stack: bool = False,
+                               acc: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """The moment sums of return_vecexcel (PP:2739-2779) over EVERY map of the batch `o` (the dict analyze_batch returned):
         two launches (pb_stats_batch pass 1 / pass 2), nothing synchronises, the means are finalised on the device. `reduce_fn`
         (e.g. batch.allreduce_sum_) is applied to each accumulator right after its pass: that is the whole exchange of a batch
-        sharded over several GPUs (SURVEY 8e). Returns device tensors acc1 [groups, PB_MAX_VARS+1, 4], acc2 [groups, PB_MAX_VARS+1, 2];
-        batch.finalize_stats turns them into N / mean / std per group and variable."""
+        sharded over several GPUs. Returns device tensors acc1 [groups, PB_MAX_VARS+1, 4], acc2 [groups, PB_MAX_VARS+1, 2]
+        (with per_stack: one leading [B] axis more, a set per stack); batch.finalize_stats turns them into N / mean / std per group
+        and variable. `acc` = caller-provided zeroed accumulators (e.g. slices of a larger buffer)."""
         names = VAR_NAMES[p.method]
         B, H, W = o['intmap'].shape
         ng = len(o['roi_indices'])
         N = o['_keep'][0].shape[1]
         pp = self._params(p, self._dtype_name(o['_keep'][0]), N, H, W)
-        acc1 = torch.zeros((ng, _cabi.PB_MAX_VARS + 1, 4), dtype=torch.float64, device=self.device)
-        acc2 = torch.zeros((ng, _cabi.PB_MAX_VARS + 1, 2), dtype=torch.float64, device=self.device)
+        lead = (B,) if per_stack else ()
+        if acc is not None:
+            acc1, acc2 = acc
+        else:
+            acc1 = torch.zeros(lead + (ng, _cabi.PB_MAX_VARS + 1, 4), dtype=torch.float64, device=self.device)
+            acc2 = torch.zeros(lead + (ng, _cabi.PB_MAX_VARS + 1, 2), dtype=torch.float64, device=self.device)
         outs = (PbOutputs * B)()
         for b in range(B):
             for k, n in enumerate(names):
                 outs[b].var[k] = o['vars'][n][b].data_ptr()
             outs[b].intmap = o['intmap'][b].data_ptr()
         roi_dev = o['_keep'][1]
-        for npass, acc in ((1, acc1), (2, acc2)):
-            self._ck(self.lib.pb_stats_batch(self._ctx, C.byref(pp), npass, outs, B, _ptr(roi_dev), acc1.data_ptr(), acc2.data_ptr(),
+        for npass, acc_ in ((1, acc1), (2, acc2)):
+            self._ck(self.lib.pb_stats_batch(self._ctx, C.byref(pp), npass, int(per_stack), outs, B, _ptr(roi_dev), acc1.data_ptr(), acc2.data_ptr(),
                                              self._stream()), 'pb_stats_batch')
             if reduce_fn is not None:
-                reduce_fn(acc)
+                reduce_fn(acc_)
         return acc1, acc2
 
     # ---- "next" row N4 (SURVEY 8f): the result writers' boolean-mask gathers, on the device ---------------------------

@@ -35,7 +35,7 @@ cudaError_t pb_launch_dark_cells(const void *plane0, int dtype, int W, int ny, i
 cudaError_t pb_launch_dark_cell_all(const void *stack, int dtype, long long P, int W, int N, int y0, int x0, int cell,
                                     unsigned long long *out, cudaStream_t st);
 cudaError_t pb_launch_stats_batch(int pass, const pb_outputs *outs_dev, int n_stacks, const uint32_t *roi_bits, long long P, int n_vars, int f64,
-                                  double rot_fig, const uint32_t *group_bits, int n_groups, double *acc1, double *acc2, cudaStream_t st);
+                                  double rot_fig, const uint32_t *group_bits, int n_groups, int per_stack, double *acc1, double *acc2, cudaStream_t st);
 bool pb_march_supported(const pb_params *p);
 cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches);
 
@@ -54,7 +54,11 @@ struct pb_ctx {
     int device = 0;
     std::string err;
     long launches = 0;
-    // calibration
+    // calibration: `lut_block` holds n_disks tables back to back (each: table | grid | (h, 1/h)); lut_dev / grid_dev / hy_dev
+    // point into the selected one
+    char *lut_block = nullptr;
+    size_t lut_stride = 0;
+    int n_disks = 0, cur_disk = 0;
     double2 *lut_dev = nullptr;
     double *grid_dev = nullptr;
     double2 *hy_dev = nullptr;
@@ -164,7 +168,7 @@ int pb_destroy(pb_ctx *ctx) {
     if (!ctx) return PB_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->lut_dev); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
+    cudaFree(ctx->lut_block); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); }
     if (ctx->hist_pinned) cudaFreeHost(ctx->hist_pinned);
@@ -176,9 +180,18 @@ int pb_destroy(pb_ctx *ctx) {
 const char *pb_last_error(const pb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 long pb_launch_count(const pb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, const double *grid) {
-    if (!ctx || !rho || !psi || !grid || n < 2) return fail(ctx, PB_ERR_ARG, "pb_set_diskcone: bad argument");
-    // validate first: a rejected call leaves the previous table in place.
+static void select_disk(pb_ctx *ctx, int d) {
+    const size_t b_t = sizeof(double2) * (size_t)ctx->lut_n * ctx->lut_n, b_g = (sizeof(double) * ctx->lut_n + 15) & ~(size_t)15;
+    char *blk = ctx->lut_block + (size_t)d * ctx->lut_stride;
+    ctx->lut_dev = reinterpret_cast<double2 *>(blk);
+    ctx->grid_dev = reinterpret_cast<double *>(blk + b_t);
+    ctx->hy_dev = reinterpret_cast<double2 *>(blk + b_t + b_g);
+    ctx->cur_disk = d;
+}
+
+int pb_set_diskcones(pb_ctx *ctx, int n_disks, const double *rho, const double *psi, int n, const double *grid) {
+    if (!ctx || !rho || !psi || !grid || n < 2 || n_disks < 1 || n_disks > 4096) return fail(ctx, PB_ERR_ARG, "pb_set_diskcones: bad argument");
+    // validate first: a rejected call leaves the previous tables in place.
     // The cell search corrects an arithmetic guess by at most one cell: the grid must be (numerically) uniform, as the
     // reference's always is (np.linspace(-1, 1, NbMapValues), PC:463)
     {
@@ -194,23 +207,41 @@ int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, co
         if (!(hy[k].x > 0.0)) return fail(ctx, PB_ERR_ARG, "pb_set_diskcone: grid must be strictly increasing");
     }
     CK(cudaSetDevice(ctx->device));
-    std::vector<double2> t((size_t)n * n);
-    for (size_t k = 0; k < t.size(); ++k) { t[k].x = rho[k]; t[k].y = psi[k]; }
-    // one allocation: table | grid | (h, 1/h); uploaded before the old one is released
-    const size_t b_t = sizeof(double2) * t.size(), b_g = (sizeof(double) * n + 15) & ~(size_t)15, b_h = sizeof(double2) * hy.size();
+    // one allocation for all disks, each: table | grid | (h, 1/h); uploaded before the old set is released
+    const size_t nn = (size_t)n * n;
+    const size_t b_t = sizeof(double2) * nn, b_g = (sizeof(double) * n + 15) & ~(size_t)15, b_h = (sizeof(double2) * hy.size() + 255) & ~(size_t)255;
+    const size_t stride = b_t + b_g + b_h;
     char *blk = nullptr;
-    CK(cudaMalloc(&blk, b_t + b_g + b_h));
-    cudaError_t e_ = cudaMemcpy(blk, t.data(), b_t, cudaMemcpyHostToDevice);
-    if (e_ == cudaSuccess) e_ = cudaMemcpy(blk + b_t, grid, sizeof(double) * n, cudaMemcpyHostToDevice);
-    if (e_ == cudaSuccess) e_ = cudaMemcpy(blk + b_t + b_g, hy.data(), b_h, cudaMemcpyHostToDevice);
-    if (e_ == cudaSuccess && ctx->lut_dev) e_ = cudaDeviceSynchronize();   // kernels already enqueued may still read the old table
-    if (e_ != cudaSuccess) { cudaFree(blk); ctx->err = std::string("pb_set_diskcone: ") + cudaGetErrorString(e_); return PB_ERR_CUDA; }
-    if (ctx->lut_dev) cudaFree(ctx->lut_dev);
-    ctx->lut_dev = reinterpret_cast<double2 *>(blk);
-    ctx->grid_dev = reinterpret_cast<double *>(blk + b_t);
-    ctx->hy_dev = reinterpret_cast<double2 *>(blk + b_t + b_g);
+    CK(cudaMalloc(&blk, stride * n_disks));
+    std::vector<double2> t(nn);
+    cudaError_t e_ = cudaSuccess;
+    for (int d = 0; d < n_disks && e_ == cudaSuccess; ++d) {
+        const double *r = rho + (size_t)d * nn, *q = psi + (size_t)d * nn;
+        for (size_t k = 0; k < nn; ++k) { t[k].x = r[k]; t[k].y = q[k]; }
+        char *dst = blk + (size_t)d * stride;
+        e_ = cudaMemcpy(dst, t.data(), b_t, cudaMemcpyHostToDevice);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(dst + b_t, grid, sizeof(double) * n, cudaMemcpyHostToDevice);
+        if (e_ == cudaSuccess) e_ = cudaMemcpy(dst + b_t + b_g, hy.data(), sizeof(double2) * hy.size(), cudaMemcpyHostToDevice);
+    }
+    if (e_ == cudaSuccess && ctx->lut_block) e_ = cudaDeviceSynchronize();   // kernels already enqueued may still read the old tables
+    if (e_ != cudaSuccess) { cudaFree(blk); ctx->err = std::string("pb_set_diskcones: ") + cudaGetErrorString(e_); return PB_ERR_CUDA; }
+    if (ctx->lut_block) cudaFree(ctx->lut_block);
+    ctx->lut_block = blk;
+    ctx->lut_stride = stride;
+    ctx->n_disks = n_disks;
     ctx->lut_n = n;
     ctx->grid_lo = grid[0]; ctx->grid_hi = grid[n - 1];
+    select_disk(ctx, 0);
+    return PB_OK;
+}
+
+int pb_set_diskcone(pb_ctx *ctx, const double *rho, const double *psi, int n, const double *grid) {
+    return pb_set_diskcones(ctx, 1, rho, psi, n, grid);
+}
+
+int pb_select_diskcone(pb_ctx *ctx, int disk) {
+    if (!ctx || disk < 0 || disk >= ctx->n_disks) return fail(ctx, PB_ERR_ARG, "pb_select_diskcone: no such resident disk cone");
+    select_disk(ctx, disk);      // host-side pointer switch only: kernels already enqueued keep the table they were launched with
     return PB_OK;
 }
 
@@ -593,7 +624,7 @@ int pb_stats(pb_ctx *ctx, const void *values, const void *rho, int is_f64, const
     return ws_release(ctx, st);
 }
 
-int pb_stats_batch(pb_ctx *ctx, const pb_params *p, int pass, const pb_outputs *outs_host, int n_stacks, const uint32_t *roi_bits,
+int pb_stats_batch(pb_ctx *ctx, const pb_params *p, int pass, int per_stack, const pb_outputs *outs_host, int n_stacks, const uint32_t *roi_bits,
                    double *acc1_dev, double *acc2_dev, void *stream) {
     if (!ctx || !p || !outs_host || !acc1_dev || !acc2_dev || n_stacks < 1 || (pass != 1 && pass != 2))
         return fail(ctx, PB_ERR_ARG, "pb_stats_batch: bad argument");
@@ -610,7 +641,7 @@ int pb_stats_batch(pb_ctx *ctx, const pb_params *p, int pass, const pb_outputs *
     int rc;
     if ((rc = push_outs(ctx, outs_host, n_stacks, st, &od))) return rc;
     CK(pb_launch_stats_batch(pass, od, n_stacks, roi_bits, (long long)p->H * p->W, nv, (p->flags & PB_FLAG_OUT_F64) ? 1 : 0, p->rotation_fig,
-                             ctx->group_bits, ctx->n_groups, acc1_dev, acc2_dev, st));
+                             ctx->group_bits, ctx->n_groups, per_stack, acc1_dev, acc2_dev, st));
     ctx->launches++;
     return PB_OK;
 }

@@ -50,7 +50,13 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
     else if (k < nb - 1 && d >= e[k + 1]) ++k;
     unsigned *c = h.cnt + var * nb + k;
     if (a.simple) {
-        atomicAdd(c, 1u);
+        if (a.flags & PB_FLAG_HIST_MATCH) {
+            // lanes of this warp that update the same counter elect one of them, which adds their number
+            const unsigned peers = __match_any_sync(__activemask(), var * nb + k);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(c, (unsigned)__popc(peers));
+        } else {
+            atomicAdd(c, 1u);
+        }
     } else if (a.n_groups == 1) {
         if (bits & a.group_bits[0]) atomicAdd(c, 1u);
     } else {

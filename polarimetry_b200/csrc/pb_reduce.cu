@@ -103,7 +103,7 @@ struct StatsBatchArgs {
     const uint32_t *roi_bits;    // [P] or NULL
     long long P;
     int n_vars;                  // primary variables (Rho first); statistic slot n_vars is intmap
-    int f64;
+    int f64, per_stack, n_groups;
     double rot_fig;
     uint32_t group_bits[PB_MAX_ROIS];
 };
@@ -114,6 +114,10 @@ __global__ void __launch_bounds__(256) k_stats_batch(StatsBatchArgs a, double *_
     __shared__ double sh[8];
     const int g = blockIdx.z;
     const pb_outputs o = a.outs[blockIdx.y];
+    if (a.per_stack) {                          // one accumulator set per stack instead of one for the whole batch
+        acc1 += (size_t)blockIdx.y * a.n_groups * SB_SLOTS * 4;
+        acc2 += (size_t)blockIdx.y * a.n_groups * SB_SLOTS * 2;
+    }
     const uint32_t gb = a.group_bits[g];
     const T *maps[SB_SLOTS];
 #pragma unroll
@@ -301,9 +305,9 @@ cudaError_t pb_launch_fit_maps(const double *f, const uint8_t *mask, long long P
 }
 
 cudaError_t pb_launch_stats_batch(int pass, const pb_outputs *outs_dev, int n_stacks, const uint32_t *roi_bits, long long P, int n_vars, int f64,
-                                  double rot_fig, const uint32_t *group_bits, int n_groups, double *acc1, double *acc2, cudaStream_t st) {
+                                  double rot_fig, const uint32_t *group_bits, int n_groups, int per_stack, double *acc1, double *acc2, cudaStream_t st) {
     StatsBatchArgs a;
-    a.outs = outs_dev; a.roi_bits = roi_bits; a.P = P; a.n_vars = n_vars; a.f64 = f64; a.rot_fig = rot_fig;
+    a.outs = outs_dev; a.roi_bits = roi_bits; a.P = P; a.n_vars = n_vars; a.f64 = f64; a.rot_fig = rot_fig; a.per_stack = per_stack; a.n_groups = n_groups;
     for (int g = 0; g < PB_MAX_ROIS; ++g) a.group_bits[g] = g < n_groups ? group_bits[g] : 0u;
     int bx = (int)((P + 255) / 256 < 148LL * 4 ? (P + 255) / 256 : 148LL * 4);
     if (bx < 1) bx = 1;

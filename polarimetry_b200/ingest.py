@@ -33,7 +33,7 @@ def _probe(file) -> tuple:
     """(n_pages, height, width, numpy dtype) of a multi-page TIFF, through the reference's reader."""
     import cv2
     n = cv2.imcount(str(file), cv2.IMREAD_ANYDEPTH)
-    ok, pg = cv2.imreadmulti(str(file), [], 0, 1, cv2.IMREAD_ANYDEPTH)
+    ok, pg = cv2.imreadmulti(str(file), 0, 1, flags=cv2.IMREAD_ANYDEPTH)
     if n < 1 or not ok or not len(pg):
         raise FileNotFoundError(f'cannot read {file}')
     return n, pg[0].shape[0], pg[0].shape[1], pg[0].dtype, pg[0]
@@ -102,7 +102,7 @@ class FolderAnalyzer:
                         if page == 0:
                             pg = first
                         else:
-                            ok, pgs = cv2.imreadmulti(str(files[k]), [], page, 1, cv2.IMREAD_ANYDEPTH)
+                            ok, pgs = cv2.imreadmulti(str(files[k]), page, 1, flags=cv2.IMREAD_ANYDEPTH)
                             if not ok or not len(pgs):
                                 raise IOError(f'{files[k]}: page {page} unreadable')
                             pg = pgs[0]

@@ -12,17 +12,19 @@ K_TH_3D = np.array([[0.3530, 0.0030, 0.0750, 0.0], [0.0030, 0.3530, 0.0750, 0.0]
 K_TH_2D = np.array([[0.4770, 0.0230, 0.0], [0.0230, 0.4770, 0.0], [0.2500, 0.2500, 0.4540], [0.2500, 0.2500, -0.4540]])
 
 
-def _grid(H, W):
+def _grid(H, W, rho_lo: float = 0.0, rho_span: float = 180.0):
     yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
-    rho0 = np.deg2rad((180.0 * xx / W) % 180.0)
+    rho0 = np.deg2rad((rho_lo + rho_span * xx / W) % 180.0)
     return yy, xx, rho0
 
 
 def stack_1pf(H: int, W: int, N: int = 18, seed: int = 0, dark: int = 480, dtype=np.uint16,
-              level: float = 2000.0, amp: float = 1500.0) -> np.ndarray:
-    """G1: one-photon fluorescence stack, orientation sweeping along x, modulation depth along y."""
+              level: float = 2000.0, amp: float = 1500.0, rho_lo: float = 0.0, rho_span: float = 180.0) -> np.ndarray:
+    """G1: one-photon fluorescence stack, orientation sweeping along x (over [rho_lo, rho_lo + rho_span) degrees: the default
+    covers every orientation; a span of a few degrees is an aligned fibre, all of whose pixels fall into two or three
+    histogram bins), modulation depth along y."""
     rng = np.random.default_rng(seed)
-    yy, xx, rho0 = _grid(H, W)
+    yy, xx, rho0 = _grid(H, W, rho_lo, rho_span)
     m = 0.05 + 0.9 * yy / H
     I0 = level + amp * np.sin(xx / 37.0) * np.cos(yy / 53.0)
     alpha = (-np.pi * np.arange(N) / N)[:, None, None]

@@ -97,6 +97,34 @@ def test_4polar3d_4x2048x2048_configs2(eng):
         ref = rs.analyze_stack(v, rs.Params(**p), rs.Calib.from_K(K), want_stats=False)
         assert ref['mask'].mean() > 0.3
         compare(res, ref, exact_maps=False, p=rs.Params(**p))
+        same_decisions_in_float32_mode(eng, v, p, Calibration.from_K(K), res)
+
+
+def same_decisions_in_float32_mode(eng, v, p, cal, res64):
+    """float32-output mode runs the certified fast evaluation of the 4POLAR angles: the mask and EVERY histogram count must be
+    those of the double-precision mode (decisions are only taken from a fast value when its error bound proves them), the maps
+    within 1e-3 degrees (north_star)."""
+    r32 = eng.analyze(v, AnalysisParams(out_dtype='float32', **p), cal)
+    assert util.eq(r32.mask.cpu().numpy(), res64.mask.cpu().numpy())
+    for k, h in r32.hist.items():
+        assert util.eq(h, res64.hist[k]), k
+    for a, b in zip(r32.vars, res64.vars):
+        x, y = a.values.cpu().numpy().astype(np.float64), b.values.cpu().numpy()
+        assert util.eq(np.isnan(x), np.isnan(y)), a.name
+        m = np.isfinite(y)
+        d = util.circ_diff(x[m], y[m]) if a.name == 'Rho' else np.abs(x[m] - y[m])
+        assert d.max(initial=0.0) <= 1e-3, (a.name, d.max())
+
+
+def test_4polar2d_fast_path_decisions(eng):
+    v = synth.stack_4polar(1024, 1024, seed=5, three_d=False)
+    K = util.load_K('Calib_th_2D')
+    for kw in (dict(bins=(1, 1)), dict(bins=(2, 2), rotation=(33.0, 12.0, 0.0))):
+        p = dict(method='4POLAR 2D', dark=0.0, ilow=1000.0, **kw)
+        res = eng.analyze(v, AnalysisParams(**p), Calibration.from_K(K))
+        ref = rs.analyze_stack(v, rs.Params(**p), rs.Calib.from_K(K), want_stats=False)
+        compare(res, ref, exact_maps=False, p=rs.Params(**p))
+        same_decisions_in_float32_mode(eng, v, p, Calibration.from_K(K), res)
 
 
 def test_two_temporary_calibrations_back_to_back(eng):

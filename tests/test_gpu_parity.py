@@ -499,7 +499,7 @@ def test_batch_statistics_over_two_shards(eng, method):
                 po[b].var[k] = o['vars'][n][b].data_ptr()
             po[b].intmap = o['intmap'][b].data_ptr()
         pp = eng._params(p, 'uint16', stacks.shape[1], H, W)
-        eng._ck(eng.lib.pb_stats_batch(eng._ctx, C.byref(pp), npass, po, Bs, o['_keep'][1].data_ptr(), acc1.data_ptr(), acc2.data_ptr(),
+        eng._ck(eng.lib.pb_stats_batch(eng._ctx, C.byref(pp), npass, 0, po, Bs, o['_keep'][1].data_ptr(), acc1.data_ptr(), acc2.data_ptr(),
                                        eng._stream()), 'pb_stats_batch')
 
     ng = len(outs[0]['roi_indices'])
@@ -524,3 +524,20 @@ def test_batch_statistics_over_two_shards(eng, method):
                 continue
             assert rs.fmt3(float(rows[g][k])) == rs.fmt3(float(v)), (g, k, rows[g][k], v)
             assert abs(rows[g][k] - v) <= 1e-9 * max(1.0, abs(v)), (g, k)
+
+
+def test_histogram_match_aggregation_on_an_aligned_sample(eng):
+    """PB_FLAG_HIST_MATCH (one shared-memory atomic per distinct bin of a warp) on a sample whose rho falls into two or three bins:
+    identical histograms and maps, with and without the flag, fused pixel and fused march plans; and equal to the oracle."""
+    from polarimetry_b200 import synth
+    v = synth.stack_1pf(96, 128, 18, seed=9, rho_lo=40.0, rho_span=5.0)
+    cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
+    for bins in ((1, 1), (3, 3)):
+        a = eng.analyze(v, AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=30000.0), cal)
+        b = eng.analyze(v, AnalysisParams(method='1PF', dark=480.0, bins=bins, ilow=30000.0, hist_match=True), cal)
+        ref = rs.analyze_stack(v, rs.Params(method='1PF', dark=480.0, bins=bins, ilow=30000.0), util.load_disk(cases.DISK_NODIST), want_stats=False)
+        for k in a.hist:
+            assert util.eq(a.hist[k], b.hist[k]) and util.eq(a.hist[k], ref['hist'][k]), (bins, k)
+        assert (ref['hist'][('Rho', None)] > 0).sum() <= 4
+        for va, vb in zip(a.vars, b.vars):
+            assert util.eq(va.values.cpu().numpy(), vb.values.cpu().numpy())

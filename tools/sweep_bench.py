@@ -41,12 +41,17 @@ def full():
         eng.analyze_batch(stacks, p, cal, want_intensity=False, out=oa)
 def once():
     proj = eng.project(stacks, p)
+    if any(c.uid not in getattr(eng, '_resident', {}) for c in disks):
+        eng.set_diskcones(disks)             # every disk cone of the sweep resident: switching is a pointer change
     for cal in disks:
         eng.lut_apply(proj, p, cal, out=ob)
 t_full, t_once = timed(full), timed(once)
+def sweep_rows():
+    return eng.calibration_sweep(list(stacks), disks, p)
+t_rows = timed(sweep_rows, reps=2)
 # same results for the last disk
 full(); once(); torch.cuda.synchronize()
 same = all(torch.equal(oa['vars'][n].nan_to_num(-1.0), ob['vars'][n].nan_to_num(-1.0)) for n in ('Rho', 'Psi')) and torch.equal(oa['hist'], ob['hist'])
 print(json.dumps({'workload': f'calibration sweep: {a.disks} disk cones x {a.stacks} resident 1PF stacks {H}x{W}x{N} uint16, bin {a.bin}x{a.bin}',
-                  'full_analysis_per_disk_ms': t_full, 'project_once_ms': t_once, 'speedup': t_full / t_once, 'identical_last_disk': bool(same),
+                  'full_analysis_per_disk_ms': t_full, 'project_once_ms': t_once, 'speedup': t_full / t_once, 'identical_last_disk': bool(same), 'sweep_with_statistics_rows_ms': t_rows,
                   'ms_per_disk_stack_full': t_full / (a.disks * a.stacks), 'ms_per_disk_stack_once': t_once / (a.disks * a.stacks)}))
