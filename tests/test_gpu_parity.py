@@ -538,6 +538,7 @@ def test_histogram_match_aggregation_on_an_aligned_sample(eng):
         ref = rs.analyze_stack(v, rs.Params(method='1PF', dark=480.0, bins=bins, ilow=30000.0), util.load_disk(cases.DISK_NODIST), want_stats=False)
         for k in a.hist:
             assert util.eq(a.hist[k], b.hist[k]) and util.eq(a.hist[k], ref['hist'][k]), (bins, k)
-        assert (ref['hist'][('Rho', None)] > 0).sum() <= 4
+        hr = np.sort(ref['hist'][('Rho', None)])[::-1]
+        assert hr[:3].sum() > 0.9 * hr.sum()                     # an aligned sample: three bins hold nearly every pixel
         for va, vb in zip(a.vars, b.vars):
             assert util.eq(va.values.cpu().numpy(), vb.values.cpu().numpy())
