@@ -146,6 +146,8 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
             const int L = p * TR + rr;
             *reinterpret_cast<uint16_t *>(raw + swz(L, cc >> 3) + (cc & 7) * 2) = v;
         }
+        // these generic-proxy stores are later overwritten by the TMA (async proxy) when the stage is refilled
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     };
     // ---- T tile of tile u: per tile position the sum over the planes of max(v, dark) (PC:261 up to the constant N*dark)
     unsigned char *const Tt = smem + ta.off_T;
@@ -417,25 +419,32 @@ cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int 
     return cudaGetLastError();
 }
 
-// rows per CTA: the largest of 16 / 8 / 4 whose (N + 1) * MR lines fit a CTA of at most PB_TMA_MAX_LINES threads (N = 90, the
-// configs[4] shape: 8 rows, 728 threads, measured 346 k against 325 k Mpx-angles/s with 4 rows). The march of a
-// row block is sequential over W, so fewer rows per CTA do not shorten a single-stack call (measured, one 2048x2048x18 stack:
-// 16 rows 0.47 ms, 8 rows 0.71 ms, 4 rows 0.70 ms): the grid size plays no role in the choice.
+// rows per CTA (16 / 8 / 4). The march of a row block is sequential over W, so fewer rows per CTA do not shorten a single-stack
+// call (measured, one 2048x2048x18 stack: 16 rows 0.47 ms, 8 rows 0.71 ms, 4 rows 0.70 ms): the grid size plays no role.
+// Chosen: the largest MR whose CTA leaves room for three resident CTAs per SM (<= 75 KB of shared memory: N = 18 -> 16 rows,
+// SHG's N = 36 -> 8 rows, measured 314 k against 270 k Mpx-angles/s with 16 rows = one CTA per SM); if none does, the largest
+// that fits at all (N = 90, the configs[4] shape: 8 rows, 728 threads, 346 k against 325 k with 4 rows).
 #ifndef PB_TMA_MAX_LINES
 #define PB_TMA_MAX_LINES 768
 #endif
-inline int rows_for(int N, int H, int n_stacks) {
+template <int BW>
+int rows_for(const PixArgs &a) {
     static const int forced = [] { const char *e = getenv("PB_TMA_ROWS"); return e ? atoi(e) : 0; }();
     if (forced == 16 || forced == 8 || forced == 4) return forced;
-    (void)H; (void)n_stacks;
-    int mr = 16;
-    while (mr > 4 && (N + 1) * mr > PB_TMA_MAX_LINES) mr /= 2;
-    return mr;
+    TmaArgs t;
+    const size_t s16 = plan<BW, 16>(a, t), s8 = plan<BW, 8>(a, t), s4 = plan<BW, 4>(a, t);
+    const size_t sz[3] = {s16, s8, s4};
+    const int mr[3] = {16, 8, 4};
+    for (int k = 0; k < 3; ++k)
+        if (sz[k] && sz[k] <= 75 * 1024 && (a.N + 1) * mr[k] <= PB_TMA_MAX_LINES) return mr[k];
+    for (int k = 0; k < 3; ++k)
+        if (sz[k] && (a.N + 1) * mr[k] <= PB_TMA_MAX_LINES) return mr[k];
+    return 4;
 }
 
 template <int NH, int BW>
 cudaError_t launch_bw(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st) {
-    const int mr = rows_for(a.N, a.H, n_stacks);
+    const int mr = rows_for<BW>(a);
     // the reference's standard 1PF acquisition (18 angles, PP:1926) with the small windows has fully unrolled variants
     if constexpr (NH == 1 && BW <= 5) {
         if (a.N == 18) {
