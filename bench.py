@@ -558,8 +558,12 @@ def main():
            'api': 'Engine.analyze_host -> pb_analyze_host (pinned host buffers, 2-stream copy/compute overlap)'}
 
     # size-independent sanity of the timed outputs: every valid pixel has a rho inside [0, 180] -> one histogram count each
+    # (the histograms were summed over the ranks by the step's all-reduce: compare with the valid pixels of all ranks)
     hist_np = out['hist'].cpu().numpy()
-    n_valid = int(out['mask'].sum().item())
+    nv = out['mask'].sum().to(torch.int64).reshape(1)
+    if world > 1:
+        dist.all_reduce(nv)
+    n_valid = int(nv.item())
     assert int(hist_np[0, 0, 0].sum()) == n_valid, (int(hist_np[0, 0, 0].sum()), n_valid)
 
     cpu = parity = None

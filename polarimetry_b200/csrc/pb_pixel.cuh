@@ -96,16 +96,34 @@ __device__ __forceinline__ int lut_axis(const double *__restrict__ g, const doub
 
 // bilinear interpolation of the interleaved (rho, psi) table in the reference's evaluation order
 // (SURVEY 8a row a6): v = 0 + V00 w00 + V01 w01 + V10 w10 + V11 w11, w = ((1)(1-t0))(1-t1) ... ; NaN corners propagate.
+// The cell is first GUESSED arithmetically (exact up to one cell for the linspace grid) and everything that depends on it -- grid
+// values, the (h, 1/h) entries and the four table corners -- is loaded at once, so the lookup costs one memory latency instead of
+// three dependent ones; the guess is then verified against the real grid values and the rare miss takes the searched path.
 __device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y, double &rho, double &psi) {
     rho = pb_nan(); psi = pb_nan();
     if (!(x >= a.grid_lo && x <= a.grid_hi && y >= a.grid_lo && y <= a.grid_hi)) return;   // out of range or NaN -> fill value NaN
     const int n = a.lut_n;
+    int i0 = max(0, min(__double2int_rd(fma(x, a.half_nm1, a.half_nm1)), n - 2));
+    int i1 = max(0, min(__double2int_rd(fma(y, a.half_nm1, a.half_nm1)), n - 2));
+    const double ga0 = __ldg(a.grid + i0), gb0 = __ldg(a.grid + i0 + 1), ga1 = __ldg(a.grid + i1), gb1 = __ldg(a.grid + i1 + 1);
+    const double2 c0 = __ldg(a.lut_hy + i0), c1 = __ldg(a.lut_hy + i1);
+    const double2 *T = a.lut + (i0 * n + i1);
+    double2 v00 = __ldg(T), v01 = __ldg(T + 1), v10 = __ldg(T + n), v11 = __ldg(T + n + 1);
     double t0, t1;
-    const int i0 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, x, t0), i1 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, y, t1);
+    if (x >= ga0 && (x < gb0 || i0 == n - 2) && y >= ga1 && (y < gb1 || i1 == n - 2)) {
+        // t = (x - ga) / (gb - ga), correctly rounded from the tabulated spacing h = gb - ga and y = RN(1/h)
+        // (Markstein: q0 = RN(d y), r = d - q0 h exactly, t = RN(q0 + r y); tests/test_shortcuts.py)
+        const double d0 = x - ga0, q0 = d0 * c0.y, d1 = y - ga1, q1 = d1 * c1.y;
+        t0 = fma(fma(-q0, c0.x, d0), c0.y, q0);
+        t1 = fma(fma(-q1, c1.x, d1), c1.y, q1);
+    } else {
+        i0 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, x, t0);
+        i1 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, y, t1);
+        T = a.lut + (i0 * n + i1);
+        v00 = __ldg(T); v01 = __ldg(T + 1); v10 = __ldg(T + n); v11 = __ldg(T + n + 1);
+    }
     const double u0 = 1.0 - t0, u1 = 1.0 - t1;
     const double w00 = u0 * u1, w01 = u0 * t1, w10 = t0 * u1, w11 = t0 * t1;    // (1.0 * u0) == u0 exactly
-    const double2 *T = a.lut + (i0 * n + i1);
-    const double2 v00 = __ldg(T), v01 = __ldg(T + 1), v10 = __ldg(T + n), v11 = __ldg(T + n + 1);
     // 0.0 + p == p for every p that can matter here (p = -0.0 only for a zero table entry times a zero weight)
     double r = v00.x * w00, q = v00.y * w00;
     r = r + v01.x * w01; q = q + v01.y * w01;
