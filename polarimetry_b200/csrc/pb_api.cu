@@ -37,7 +37,7 @@ cudaError_t pb_launch_dark_cell_all(const void *stack, int dtype, long long P, i
 cudaError_t pb_launch_stats_batch(int pass, const pb_outputs *outs_dev, int n_stacks, const uint32_t *roi_bits, long long P, int n_vars, int f64,
                                   double rot_fig, const uint32_t *group_bits, int n_groups, int per_stack, double *acc1, double *acc2, cudaStream_t st);
 bool pb_march_supported(const pb_params *p);
-cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches);
+cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches, unsigned char *redo);
 
 static std::string g_create_error;
 
@@ -88,7 +88,27 @@ struct pb_ctx {
     int64_t *hist_pinned = nullptr;   // pinned staging of the per-stack histograms of pb_analyze_host
     size_t hist_pinned_n = 0;
     cudaEvent_t ws_event = nullptr;   // recorded after the last kernel that used the shared workspace
+    // strip-march redo flags (one byte per 16-row block per stack): a ring of slots, one per call, so that calls in flight on
+    // different streams (pb_analyze_host's two pipelines) never share one
+    unsigned char *redo_dev = nullptr;
+    size_t redo_slot_bytes = 0;
+    int redo_pos = 0;
 };
+static const int PB_REDO_SLOTS = 8;
+
+// flags buffer of one fused-march call (n_stacks x ceil(H/16) bytes); grows with a device synchronisation
+static unsigned char *redo_slot(pb_ctx *ctx, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > ctx->redo_slot_bytes) {
+        if (cudaDeviceSynchronize() != cudaSuccess) return nullptr;
+        if (ctx->redo_dev) cudaFree(ctx->redo_dev);
+        ctx->redo_dev = nullptr; ctx->redo_slot_bytes = 0;
+        if (cudaMalloc(&ctx->redo_dev, bytes * PB_REDO_SLOTS) != cudaSuccess) return nullptr;
+        ctx->redo_slot_bytes = bytes;
+    }
+    ctx->redo_pos = (ctx->redo_pos + 1) % PB_REDO_SLOTS;
+    return ctx->redo_dev + (size_t)ctx->redo_pos * ctx->redo_slot_bytes;
+}
 
 #define CK(call)                                                                                     \
     do {                                                                                             \
@@ -168,7 +188,7 @@ int pb_destroy(pb_ctx *ctx) {
     if (!ctx) return PB_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->lut_block); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev);
+    cudaFree(ctx->lut_block); cudaFree(ctx->edges_dev); cudaFree(ctx->outs_dev); cudaFree(ctx->acc_dev); cudaFree(ctx->redo_dev);
     for (int k = 0; k < 6; ++k) cudaFree(ctx->ws[k]);
     for (int k = 0; k < 2; ++k) { if (ctx->hs[k]) cudaStreamDestroy(ctx->hs[k]); }
     if (ctx->hist_pinned) cudaFreeHost(ctx->hist_pinned);
@@ -376,6 +396,7 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     memcpy(a.invk, ctx->invk, sizeof(a.invk));
     a.grid_lo = ctx->grid_lo; a.grid_hi = ctx->grid_hi; a.half_nm1 = 0.5 * (double)(ctx->lut_n - 1);
     a.simple = 0;   // set by the callers once roi_bits / mask_in are known
+    a.all_lean = 0;
 }
 
 // vector stores of the per-pixel kernels need 16-byte aligned maps (4-byte aligned mask); otherwise the scalar kernels run
@@ -387,6 +408,18 @@ static int outs_aligned(const pb_outputs *o, int n) {
         m |= (uintptr_t)o[s].mask;
     }
     return (acc % 16 == 0) && (m % 4 == 0);
+}
+
+// every stack asks for the throughput-mode output set: float32 maps of the variables + intmap + mask, nothing else
+// (the host-side twin of store_is_lean, pb_pixel.cuh)
+static int outs_lean(const pb_params *p, const pb_outputs *o, const double *edge, int n) {
+    if (p->flags & PB_FLAG_OUT_F64) return 0;
+    const int nv = method_nvars(p->method);
+    for (int s = 0; s < n; ++s) {
+        for (int v = 0; v < nv; ++v) if (!o[s].var[v]) return 0;
+        if (!o[s].intmap || !o[s].mask || o[s].intensity || o[s].rho_angle || (o[s].rho_contour && edge)) return 0;
+    }
+    return 1;
 }
 
 // copy n output descriptors into the device ring; returns device pointer
@@ -507,6 +540,7 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
     a.roi_bits = roi_bits; a.edge = edge;
     a.simple = (!roi_bits && ctx->n_rois == 0 && ctx->n_groups == 1) ? 1 : 0;
     a.out_aligned = outs_aligned(outs_host, n_stacks);
+    a.all_lean = outs_lean(p, outs_host, edge, n_stacks);
     const long long P = a.P;
     const std::string plan = plan_name(ctx, p);
     const pb_outputs *od;
@@ -517,7 +551,9 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
     }
     if (plan == "fused_march") {
         a.stack = stacks; a.stack_stride = (long long)p->N * P; a.outs = od;
-        CK(pb_launch_march(a, ctx->basis, p, n_stacks, st, &ctx->launches));
+        unsigned char *redo = redo_slot(ctx, (size_t)n_stacks * ((p->H + 15) / 16));
+        if (!redo) return fail(ctx, PB_ERR_NOMEM, "pb_analyze: cudaMalloc of the redo flags failed");
+        CK(pb_launch_march(a, ctx->basis, p, n_stacks, st, &ctx->launches, redo));
         return PB_OK;
     }
     // unfused: intensity -> box ; field -> box(H) -> box(W) ; per-pixel kernel on the double field

@@ -52,6 +52,7 @@ struct PixArgs {
     double grid_lo, grid_hi, half_nm1; // LUT grid end points and (n-1)/2
     int simple;                        // no ROI bits, no incoming mask, one histogram group: whole-image thresholding
     int out_aligned;                   // every output map of every stack is 16-byte aligned (mask: 4-byte): vector stores allowed
+    int all_lean;                      // every stack asks for the throughput-mode output set (store_is_lean) -- host evaluated
     double inv_bin_width[PB_MAX_VARS];
     double roi_ilow[PB_MAX_ROIS];
     uint32_t group_bits[PB_MAX_ROIS];

@@ -8,6 +8,8 @@ cudaError_t pb_march_u8_nh1(const PixArgs &a, const Basis1 &bs, const pb_params 
 cudaError_t pb_march_u8_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
 cudaError_t pb_march_tma_nh1(const PixArgs &a, const Basis1 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_1.cu
 cudaError_t pb_march_tma_nh2(const PixArgs &a, const Basis2 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_2.cu
+cudaError_t pb_strip_nh1(const PixArgs &a, const Basis1 &bs, int bw, int n_stacks, unsigned char *redo, cudaStream_t st);   // pb_strip_1.cu
+cudaError_t pb_march_tma_redo_nh1_bw3_n18(const PixArgs &a, const Basis1 &bs, int n_stacks, const unsigned char *redo, cudaStream_t st);
 
 // The TMA kernel (pb_march_tma.cuh) takes the common case: uint16 stacks, square windows 2..8, rows that are a multiple of 16 bytes
 // and a 16-byte aligned stack (the tensor map's stride / address rules). PB_MARCH_TMA=0 keeps the register-staged loader.
@@ -18,6 +20,14 @@ static bool tma_eligible(const PixArgs &a, const pb_params *p) {
     return true;
 }
 
+// The strip-march kernel (pb_strip.cuh: one thread per image row, every plane's filter state in registers) takes the reference's
+// standard 1PF acquisition -- 18 angles, 3x3 window -- when the TMA rules hold; pixels it cannot decide go to k_march_tma's redo pass.
+// PB_FLAG_EXACT_CHI2 (every pixel through the exact loop) and PB_STRIP=0 keep k_march_tma.
+static bool strip_eligible(const PixArgs &a, const pb_params *p, const unsigned char *redo) {
+    static const bool on = [] { const char *e = getenv("PB_STRIP"); return !e || atoi(e) != 0; }();
+    return on && redo && p->method == PB_1PF && p->N == 18 && p->bin_w == 3 && p->bin_h == 3 && a.W >= 16 && a.H >= 2 &&
+           !(p->flags & PB_FLAG_EXACT_CHI2) && tma_eligible(a, p);
+}
 
 // The march kernel covers: harmonic modalities without sqrt (1PF, SRS, SHG, 2PF), integer stacks, integer-valued
 // dark / dark+removed (so that the H pass sums integers), bin_w <= 8, N + 1 <= 32 chain warps. Everything else
@@ -46,13 +56,25 @@ bool pb_march_supported(const pb_params *p) {
     return smem <= 227 * 1024;
 }
 
-cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches) {
+cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st, long *launches,
+                            unsigned char *redo) {
     cudaError_t e;
     const bool tma_ok = tma_eligible(a, p);
     if (p->method == PB_1PF) {
         Basis1 b1;
         memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));
         memcpy(b1.kc2, bs.kc2, sizeof(b1.kc2)); memcpy(b1.ks2, bs.ks2, sizeof(b1.ks2));
+        if (strip_eligible(a, p, redo)) {
+            e = pb_strip_nh1(a, b1, p->bin_w, n_stacks, redo, st);
+            if (e == cudaSuccess) {
+                if (launches) ++*launches;
+                if (getenv("PB_STRIP_SKIP_REDO")) return e;
+                e = pb_march_tma_redo_nh1_bw3_n18(a, b1, n_stacks, redo, st);
+                if (e == cudaSuccess && launches) ++*launches;
+                return e;
+            }
+            if (e != cudaErrorInvalidConfiguration && e != cudaErrorNotSupported) return e;
+        }
         e = tma_ok ? pb_march_tma_nh1(a, b1, p->bin_w, n_stacks, st) : cudaErrorInvalidConfiguration;
         if (e == cudaErrorInvalidConfiguration || e == cudaErrorNotSupported)      // shape outside the TMA kernel's plan: register-staged loader
             e = p->dtype == PB_U8 ? pb_march_u8_nh1(a, b1, p, n_stacks, st) : pb_march_u16_nh1(a, b1, p, n_stacks, st);

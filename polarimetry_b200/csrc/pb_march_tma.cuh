@@ -41,6 +41,9 @@ struct TmaArgs {
     double b_hi, b_lo;           // double-double reciprocal of the (square) bin size
     double magic, magicT;        // 2^52 + bw*isub, 2^52 + bw*N*idark: conversion constants that also remove the clamp offsets
     unsigned off_bar, off_raw, raw_bytes, off_T, off_f;   // byte offsets in dynamic shared memory (off_raw relative to the 1024-aligned base)
+    // redo mode (second pass after k_strip, pb_strip.cuh): one flag per CTA (16-row block of a stack); unflagged CTAs exit at once, the
+    // others evaluate ONLY the pixels the certified screening leaves undecided (hp.need) -- k_strip stored all the others
+    const unsigned char *redo;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -79,6 +82,8 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     constexpr int FPD = FPB / 8;                        // filtered-tile row pitch in doubles
     constexpr int PLD = MR * FPD;                       // ... plane pitch in doubles
     extern __shared__ __align__(16) unsigned char smem[];
+    const bool redo = ta.redo != nullptr;
+    if (redo && !ta.redo[(size_t)blockIdx.y * gridDim.x + blockIdx.x]) return;
     const pb_outputs out = a.outs[blockIdx.y];
     const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
     const int N = NT ? NT : a.N, H = a.H, W = a.W;
@@ -293,12 +298,15 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                 if (a.simple) cand = I >= a.roi_ilow[0];
                 else if (a.mask_in) cand = __ldg(a.mask_in + p) != 0;
                 else cand = roi_pass(a, a.roi_bits ? __ldg(a.roi_bits + p) : 1u, I);
-                if (!cand && lean) {
+                if (redo && !cand) {
+                    // stored by k_strip
+                } else if (!cand && lean) {
                     store_invalid_lean<NH>(a, out, p);
                 } else {
                     PixOut o;
                     o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
                     o.m = false;
+                    bool emit = true;
                     if (cand) {
                         double S0 = 0.0, Sc = 0.0, Ss = 0.0, Sc4 = 0.0, Ss4 = 0.0, Sff = 0.0;
                         const double *fp = pfp;
@@ -326,10 +334,12 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                                 ex.template step<NH>(hp, pfp[i * PLD], bs.c2[i], bs.s2[i], c4, s4);
                             }
                             hp.m = ex.decide(a);
+                        } else if (redo) {
+                            emit = false;
                         }
-                        o = harm_stage_b<NH>(a, hs, do_hist, hp);
+                        if (emit) o = harm_stage_b<NH>(a, hs, do_hist, hp);
                     }
-                    store_pixel<NH>(a, out, p, o, I, f64, lean);
+                    if (emit) store_pixel<NH>(a, out, p, o, I, f64, lean);
                 }
             }
         } else if (u + 1 <= U) {
@@ -391,9 +401,10 @@ size_t plan(const PixArgs &a, TmaArgs &ta) {
 }
 
 template <int NH, int BW, int MR, int NT>
-cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st) {
+cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st, const unsigned char *redo = nullptr) {
     constexpr int TR = MR + BW - 1;
     TmaArgs ta;
+    ta.redo = redo;
     const size_t smem = plan<BW, MR>(a, ta);
     if (!smem) return cudaErrorInvalidConfiguration;
     EncodeTiledFn enc = encode_fn();

@@ -32,6 +32,8 @@ __device__ __forceinline__ void hist_flush(const PixArgs &a, const HistSmem &h, 
 }
 
 // np.histogram rule on explicit edges: [e_k, e_{k+1}), last bin closed, outside dropped. `val` must be finite.
+// SIMPLE = 1: the caller has established a.simple (whole-image thresholding, one histogram group)
+template <int SIMPLE = 0>
 __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, int var, double val, uint32_t bits) {
     double d = val;
     if ((a.hist_is_rho >> var) & 1u) {
@@ -49,7 +51,7 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
     if (d < e[k]) --k;
     else if (k < nb - 1 && d >= e[k + 1]) ++k;
     unsigned *c = h.cnt + var * nb + k;
-    if (a.simple) {
+    if (SIMPLE || a.simple) {
         if (a.flags & PB_FLAG_HIST_MATCH) {
             // lanes of this warp that update the same counter elect one of them, which adds their number
             const unsigned peers = __match_any_sync(__activemask(), var * nb + k);
@@ -226,13 +228,14 @@ __device__ __forceinline__ HarmPix harm_stage_a_core(const PixArgs &a, uint32_t 
 }
 
 // Stage B (PP:3017-3040 outputs, PP:3052, histograms) for a pixel whose fit/chi2 decision is h.m.
-template <int NH>
+// SIMPLE = 1: a.simple holds and PB_FLAG_PROJECT_ONLY is not set (established by the caller)
+template <int NH, int SIMPLE = 0>
 __device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem &hs, bool do_hist, const HarmPix &h) {
     PixOut o;
     o.v0 = o.v1 = o.v2 = o.v3 = o.a0m = pb_nan();
     o.m = false;
     if (!h.m) return o;
-    if constexpr (NH == 1) {
+    if constexpr (NH == 1 && !SIMPLE) {
         if (a.flags & PB_FLAG_PROJECT_ONLY) {      // the disk-independent part only (calibration sweep): a2, a0 and the mask of PP:3000
             o.v0 = h.a2r; o.v1 = h.a2i; o.a0m = h.a0; o.m = true;
             return o;
@@ -264,11 +267,11 @@ __device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem 
     o.m = m;
     if (m) o.a0m = h.a0;
     if (do_hist) {
-        if (pb_finite(v0)) hist_add(a, hs, 0, v0, h.bits);
-        if (pb_finite(v1)) hist_add(a, hs, 1, v1, h.bits);
+        if (pb_finite(v0)) hist_add<SIMPLE>(a, hs, 0, v0, h.bits);
+        if (pb_finite(v1)) hist_add<SIMPLE>(a, hs, 1, v1, h.bits);
         if constexpr (NH == 2) {
-            if (pb_finite(o.v2)) hist_add(a, hs, 2, o.v2, h.bits);
-            if (a.method == PB_SHG && pb_finite(o.v3)) hist_add(a, hs, 3, o.v3, h.bits);
+            if (pb_finite(o.v2)) hist_add<SIMPLE>(a, hs, 2, o.v2, h.bits);
+            if (a.method == PB_SHG && pb_finite(o.v3)) hist_add<SIMPLE>(a, hs, 3, o.v3, h.bits);
         }
     }
     return o;
