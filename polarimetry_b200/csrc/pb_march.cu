@@ -24,7 +24,7 @@ static bool tma_eligible(const PixArgs &a, const pb_params *p) {
 // standard 1PF acquisition -- 18 angles, 3x3 window -- when the TMA rules hold; pixels it cannot decide go to k_march_tma's redo pass.
 // PB_FLAG_EXACT_CHI2 (every pixel through the exact loop) and PB_STRIP=0 keep k_march_tma.
 static bool strip_eligible(const PixArgs &a, const pb_params *p, const unsigned char *redo) {
-    static const bool on = [] { const char *e = getenv("PB_STRIP"); return !e || atoi(e) != 0; }();
+    static const bool on = [] { const char *e = getenv("PB_STRIP"); return e && atoi(e) != 0; }();   // opt-in until it beats k_march_tma
     return on && redo && p->method == PB_1PF && p->N == 18 && p->bin_w == 3 && p->bin_h == 3 && a.W >= 16 && a.H >= 2 &&
            !(p->flags & PB_FLAG_EXACT_CHI2) && tma_eligible(a, p);
 }
