@@ -382,6 +382,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', help='skip the host-buffer leg')
     ap.add_argument('--rho-span', type=float, default=180.0, help='1pf: orientation range of the synthetic sample in degrees (180 = generator G1; '
                                                                   '6 = an aligned fibre whose rho falls into 2-3 histogram bins: contention variant)')
+    ap.add_argument('--strip', action='store_true', help='1pf bin 3: the strip-march kernel + redo pass (PB_FLAG_STRIP_MARCH; experimental, slower)')
     ap.add_argument('--hist-match', action='store_true', help='warp-aggregate the histogram updates with a match on the bin (PB_FLAG_HIST_MATCH)')
     a = ap.parse_args()
     if a.impl == 'reference':
@@ -412,7 +413,7 @@ def main():
         ilow = a.ilow
         if ilow is None:      # G1 threshold from the threshold image of the seed-0 stack, through the product's own seam
             ilow = g1_ilow(eng.get_intensity(gen(0), DARK, (a.bin, a.bin)).cpu().numpy())
-        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32', hist_match=a.hist_match)
+        p = AnalysisParams(method='1PF', dark=DARK, bins=(a.bin, a.bin), ilow=ilow, out_dtype='float32', hist_match=a.hist_match, strip_march=a.strip)
     elif method == 'SHG':
         cal = None
         ilow = 40000.0

@@ -55,6 +55,9 @@ typedef enum pb_dtype { PB_U8 = 0, PB_U16 = 1, PB_F32 = 2, PB_F64 = 3 } pb_dtype
 #define PB_FLAG_HIST_MATCH   32u /* warp-aggregate the shared-memory histogram updates with a match on (variable, bin) before the
                                     atomic: one atomic per distinct bin of a warp instead of one per lane (aligned samples whose
                                     rho falls into two or three bins); the default leaves the aggregation to the atomic unit */
+#define PB_FLAG_STRIP_MARCH  64u /* binned 1PF, 18 angles, 3x3 window: take the strip-march kernel (pb_strip2.cuh: two lanes per image
+                                    row carry the box-filter state of all planes in registers) + the redo pass of the row-march kernel
+                                    instead of the row-march kernel alone. Same results bit for bit; opt-in while it is the slower one. */
 
 typedef struct pb_ctx pb_ctx;
 

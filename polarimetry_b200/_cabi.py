@@ -12,7 +12,7 @@ import os
 LIB_PATH = Path(os.environ['PB_LIB']) if os.environ.get('PB_LIB') else PKG / 'libpolarb200.so'   # PB_LIB: developer A/B builds
 
 PB_MAX_ROIS, PB_MAX_VARS, PB_MAX_BINS = 32, 4, 128
-FLAG_OUT_F64, FLAG_NO_HIST, FLAG_EXACT_CHI2, FLAG_FORCE_UNFUSED, FLAG_PROJECT_ONLY, FLAG_HIST_MATCH = 1, 2, 4, 8, 16, 32
+FLAG_OUT_F64, FLAG_NO_HIST, FLAG_EXACT_CHI2, FLAG_FORCE_UNFUSED, FLAG_PROJECT_ONLY, FLAG_HIST_MATCH, FLAG_STRIP_MARCH = 1, 2, 4, 8, 16, 32, 64
 METHODS = {'1PF': 0, 'CARS': 1, 'SRS': 2, 'SHG': 3, '2PF': 4, '4POLAR 2D': 5, '4POLAR 3D': 6}
 DTYPES = {'uint8': 0, 'uint16': 1, 'float32': 2, 'float64': 3}
 

@@ -49,6 +49,7 @@ class AnalysisParams:
     out_dtype: str = 'float64'              # 'float64' (bit-comparable maps) or 'float32' (throughput mode)
     exact_chi2: bool = False                # disable the certified chi2 screening
     hist_match: bool = False                # warp-aggregate histogram updates with a match on the bin (aligned samples)
+    strip_march: bool = False               # binned 1PF 18 angles 3x3: the strip-march kernel + redo pass (same results; experimental)
     force_unfused: bool = False             # run the separate kernels instead of the fused one
 
 
@@ -272,6 +273,8 @@ class Engine:
             flags |= _cabi.FLAG_FORCE_UNFUSED
         if p.hist_match:
             flags |= _cabi.FLAG_HIST_MATCH
+        if p.strip_march:
+            flags |= _cabi.FLAG_STRIP_MARCH
         return PbParams(_cabi.METHODS[p.method], _cabi.DTYPES[dtype], N, H, W, int(p.bins[0]), int(p.bins[1]), flags,
                         float(p.dark), float(p.removed_intensity), float(p.rotation[0]), float(p.rotation[1]),
                         float(p.rotation[2]), float(p.chi2threshold), float(p.ilow))

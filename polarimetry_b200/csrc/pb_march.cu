@@ -22,10 +22,11 @@ static bool tma_eligible(const PixArgs &a, const pb_params *p) {
 
 // The strip-march kernel (pb_strip.cuh: one thread per image row, every plane's filter state in registers) takes the reference's
 // standard 1PF acquisition -- 18 angles, 3x3 window -- when the TMA rules hold; pixels it cannot decide go to k_march_tma's redo pass.
-// PB_FLAG_EXACT_CHI2 (every pixel through the exact loop) and PB_STRIP=0 keep k_march_tma.
+// Opt-in (PB_FLAG_STRIP_MARCH, or PB_STRIP=1 for every eligible call) while it is slower than k_march_tma; PB_FLAG_EXACT_CHI2 (every
+// pixel through the exact loop) keeps k_march_tma.
 static bool strip_eligible(const PixArgs &a, const pb_params *p, const unsigned char *redo) {
-    static const bool on = [] { const char *e = getenv("PB_STRIP"); return e && atoi(e) != 0; }();   // opt-in until it beats k_march_tma
-    return on && redo && p->method == PB_1PF && p->N == 18 && p->bin_w == 3 && p->bin_h == 3 && a.W >= 16 && a.H >= 2 &&
+    static const bool env_on = [] { const char *e = getenv("PB_STRIP"); return e && atoi(e) != 0; }();
+    return (env_on || (p->flags & PB_FLAG_STRIP_MARCH)) && redo && p->method == PB_1PF && p->N == 18 && p->bin_w == 3 && p->bin_h == 3 && a.W >= 16 && a.H >= 2 &&
            !(p->flags & PB_FLAG_EXACT_CHI2) && tma_eligible(a, p);
 }
 
@@ -68,7 +69,6 @@ cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params 
             e = pb_strip_nh1(a, b1, p->bin_w, n_stacks, redo, st);
             if (e == cudaSuccess) {
                 if (launches) ++*launches;
-                if (getenv("PB_STRIP_SKIP_REDO")) return e;
                 e = pb_march_tma_redo_nh1_bw3_n18(a, b1, n_stacks, redo, st);
                 if (e == cudaSuccess && launches) ++*launches;
                 return e;

@@ -63,7 +63,7 @@ def test_flag_constants_match_header():
     flags = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(PB_FLAG_[A-Z0-9_]+)\s+(\d+)u', h)}
     assert flags == {'PB_FLAG_OUT_F64': _cabi.FLAG_OUT_F64, 'PB_FLAG_NO_HIST': _cabi.FLAG_NO_HIST, 'PB_FLAG_EXACT_CHI2': _cabi.FLAG_EXACT_CHI2,
                      'PB_FLAG_FORCE_UNFUSED': _cabi.FLAG_FORCE_UNFUSED, 'PB_FLAG_PROJECT_ONLY': _cabi.FLAG_PROJECT_ONLY,
-                     'PB_FLAG_HIST_MATCH': _cabi.FLAG_HIST_MATCH}
+                     'PB_FLAG_HIST_MATCH': _cabi.FLAG_HIST_MATCH, 'PB_FLAG_STRIP_MARCH': _cabi.FLAG_STRIP_MARCH}
     m = re.search(r'typedef enum pb_dtype \{([^}]*)\}', h)
     dt = {k.strip(): int(v) for k, v in (x.split('=') for x in m.group(1).split(','))}
     assert dt == {'PB_U8': _cabi.DTYPES['uint8'], 'PB_U16': _cabi.DTYPES['uint16'], 'PB_F32': _cabi.DTYPES['float32'], 'PB_F64': _cabi.DTYPES['float64']}

@@ -1,5 +1,5 @@
-"""GPU parity of the strip-march kernel (pb_strip.cuh: one thread per image row, all 18 planes' box-filter state in registers)
-and of its redo pass: 1PF, 18 angles, 3x3 window. Bars as everywhere: masks, histograms and every 1PF map bit-exact against the
+"""GPU parity of the strip-march kernel (pb_strip2.cuh: two lanes per image row carry the box-filter state of all 18 planes in
+registers; opt-in with AnalysisParams(strip_march=True) = PB_FLAG_STRIP_MARCH) and of its redo pass: 1PF, 18 angles, 3x3 window. Bars as everywhere: masks, histograms and every 1PF map bit-exact against the
 unfused kernels and the exact-chi2 path (which never takes the strip kernel), in both output modes, on shapes that exercise the
 strip geometry: a partial last strip, the narrowest legal width, widths that are / are not a multiple of the 8-column tile pair,
 rows whose 3-row window reflects at the top and at the bottom edge."""
@@ -34,7 +34,8 @@ def same(a, b):
 def fast_equals(eng, v, kw, cal, ref):
     """The FAST variant (float32 maps + mask only, whole-image threshold: 128-bit stores, unrolled epilogue) against a Result."""
     kw = dict(kw, out_dtype='float32')
-    o = eng.analyze_batch(v[None], AnalysisParams(**kw), cal, want_intensity=False)
+    o = eng.analyze_batch(v[None], AnalysisParams(strip_march=True, **kw), cal, want_intensity=False)
+    kw.pop('strip_march', None)
     r = ref if ref.vars[0].values.dtype == torch.float32 else None
     if r is None:
         r = eng.analyze(v, AnalysisParams(force_unfused=True, **kw), cal)
@@ -53,8 +54,11 @@ def test_strip_equals_unfused_and_exact(eng, shape, out_dtype):
     v = synth.stack_1pf(H, W, 18, seed=H * 1000 + W)
     cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
     kw = dict(method='1PF', dark=480.0, bins=(3, 3), ilow=21000.0, out_dtype=out_dtype)
-    a = eng.analyze(v, AnalysisParams(**kw), cal)
+    a = eng.analyze(v, AnalysisParams(strip_march=True, **kw), cal)
     assert a.plan == 'fused_march'
+    n0 = eng.launch_count()
+    eng.analyze(v, AnalysisParams(strip_march=True, **kw), cal)
+    assert eng.launch_count() - n0 == 2                    # k_strip2 + the redo pass of k_march_tma
     b = eng.analyze(v, AnalysisParams(force_unfused=True, **kw), cal)
     c = eng.analyze(v, AnalysisParams(exact_chi2=True, **kw), cal)
     same(a, b)
@@ -76,7 +80,7 @@ def test_strip_redo_pass_on_undecidable_pixels(eng, out_dtype):
         v[:, y:y + hh, x:x + ww] = adv[:, :hh, :ww]
     cal = calib_for(util.CASE_BY_NAME['1pf_bin1x1'])
     kw = dict(method='1PF', dark=480.0, bins=(3, 3), ilow=0.0, out_dtype=out_dtype)
-    a = eng.analyze(v, AnalysisParams(**kw), cal)
+    a = eng.analyze(v, AnalysisParams(strip_march=True, **kw), cal)
     b = eng.analyze(v, AnalysisParams(force_unfused=True, **kw), cal)
     c = eng.analyze(v, AnalysisParams(exact_chi2=True, **kw), cal)
     same(a, b)
@@ -91,7 +95,7 @@ def test_strip_batch_and_removed_intensity(eng):
     stacks = np.stack([synth.stack_1pf(70, 88, 18, seed=s) for s in range(5)])
     for removed in (0.0, 37.0):
         kw = dict(method='1PF', dark=480.0, removed_intensity=removed, bins=(3, 3), ilow=21000.0, out_dtype='float32')
-        o = eng.analyze_batch(stacks, AnalysisParams(**kw), cal, want_intensity=False)       # float32 maps + mask only: the FAST variant
+        o = eng.analyze_batch(stacks, AnalysisParams(strip_march=True, **kw), cal, want_intensity=False)       # float32 maps + mask only: the FAST variant
         hsum = 0
         for s in range(5):
             r = eng.analyze(stacks[s], AnalysisParams(force_unfused=True, **kw), cal)
