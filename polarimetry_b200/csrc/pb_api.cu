@@ -74,6 +74,7 @@ struct pb_ctx {
     int n_vars = 0, nbins = 0;
     unsigned is_rho_bits = 0;
     double inv_w[PB_MAX_VARS] = {0};
+    double hist_lo[PB_MAX_VARS] = {0}, hist_hi[PB_MAX_VARS] = {0};
     // ROIs
     int n_rois = 0, n_groups = 1;
     double roi_ilow[PB_MAX_ROIS] = {0};
@@ -330,6 +331,7 @@ int pb_set_hist(pb_ctx *ctx, int n_vars, int nbins, const double *edges, const i
     for (int v = 0; v < n_vars; ++v) {
         const double *e = edges + (size_t)v * (nbins + 1);
         ctx->inv_w[v] = (double)nbins / (e[nbins] - e[0]);
+        ctx->hist_lo[v] = e[0]; ctx->hist_hi[v] = e[nbins];
         if (is_rho[v]) ctx->is_rho_bits |= 1u << v;
     }
     return PB_OK;
@@ -390,7 +392,7 @@ static void fill_args(pb_ctx *ctx, const pb_params *p, PixArgs &a) {
     a.thr_hi_n = (float)(p->chi2_threshold * p->N * (1.0 + 1e-5));
     // the screening identity needs N >= 3 (second harmonic) / N >= 5 (fourth harmonic) equally spaced angles
     if (p->N < (p->method == PB_1PF ? 3 : 5)) a.flags |= PB_FLAG_EXACT_CHI2;
-    for (int v = 0; v < PB_MAX_VARS; ++v) a.inv_bin_width[v] = ctx->inv_w[v];
+    for (int v = 0; v < PB_MAX_VARS; ++v) { a.inv_bin_width[v] = ctx->inv_w[v]; a.hist_lo[v] = ctx->hist_lo[v]; a.hist_hi[v] = ctx->hist_hi[v]; }
     for (int r = 0; r < PB_MAX_ROIS; ++r) { a.roi_ilow[r] = ctx->roi_ilow[r]; a.group_bits[r] = ctx->group_bits[r]; }
     if (ctx->n_rois == 0) a.roi_ilow[0] = p->ilow;
     memcpy(a.invk, ctx->invk, sizeof(a.invk));

@@ -54,6 +54,7 @@ struct PixArgs {
     int out_aligned;                   // every output map of every stack is 16-byte aligned (mask: 4-byte): vector stores allowed
     int all_lean;                      // every stack asks for the throughput-mode output set (store_is_lean) -- host evaluated
     double inv_bin_width[PB_MAX_VARS];
+    double hist_lo[PB_MAX_VARS], hist_hi[PB_MAX_VARS];   // first / last histogram edge of every variable
     double roi_ilow[PB_MAX_ROIS];
     uint32_t group_bits[PB_MAX_ROIS];
     double invk[16];

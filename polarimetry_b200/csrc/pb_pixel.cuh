@@ -31,7 +31,9 @@ __device__ __forceinline__ void hist_flush(const PixArgs &a, const HistSmem &h, 
     }
 }
 
-// np.histogram rule on explicit edges: [e_k, e_{k+1}), last bin closed, outside dropped. `val` must be finite.
+// np.histogram rule on explicit edges: [e_k, e_{k+1}), last bin closed, outside (and NaN / inf) dropped.
+// The first and last edge come from the constant bank; the arithmetic bin guess is verified against the two edges around it
+// (they are uniform -- np.linspace, checked by pb_set_hist -- so the guess is off by at most one bin) without a branch.
 // SIMPLE = 1: the caller has established a.simple (whole-image thresholding, one histogram group)
 template <int SIMPLE = 0>
 __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, int var, double val, uint32_t bits) {
@@ -41,15 +43,17 @@ __device__ __forceinline__ void hist_add(const PixArgs &a, const HistSmem &h, in
         if (a.rot_fig == 0.0 && d >= 0.0 && d <= 180.0) d = (d == 180.0) ? 0.0 : d;
         else d = pb_pymod(2.0 * (d + a.rot_fig), 360.0) / 2.0;
     }
-    const double *e = h.edges + var * (a.nbins + 1);
     const int nb = a.nbins;
-    if (!(d >= e[0]) || !(d <= e[nb])) return;
-    int k = (int)((d - e[0]) * a.inv_bin_width[var]);
+    const double e0 = a.hist_lo[var];
+    const bool inr = (d >= e0) && (d <= a.hist_hi[var]);          // false for NaN
+    int k = (int)((d - e0) * a.inv_bin_width[var]);               // NaN -> 0; saturates
     k = max(0, min(k, nb - 1));
-    // the arithmetic guess is verified against the real edges; they are uniform (np.linspace, checked by pb_set_hist),
-    // so the guess is off by at most one bin
-    if (d < e[k]) --k;
-    else if (k < nb - 1 && d >= e[k + 1]) ++k;
+    const double *e = h.edges + var * (nb + 1) + k;
+    const double ea = e[0], eb = e[1];
+    const bool dn = d < ea;
+    const bool up = !dn && (k < nb - 1) && (d >= eb);
+    k = k + (up ? 1 : 0) - (dn ? 1 : 0);
+    if (!inr) return;
     unsigned *c = h.cnt + var * nb + k;
     if (SIMPLE || a.simple) {
         if (a.flags & PB_FLAG_HIST_MATCH) {
@@ -315,11 +319,12 @@ __device__ __forceinline__ PixOut harm_stage_b(const PixArgs &a, const HistSmem 
     o.m = m;
     if (m) o.a0m = h.a0;
     if (do_hist) {
-        if (pb_finite(v0)) hist_add<SIMPLE>(a, hs, 0, v0, h.bits);
-        if (pb_finite(v1)) hist_add<SIMPLE>(a, hs, 1, v1, h.bits);
+        // non-finite values fall out of every histogram range (hist_add drops them)
+        hist_add<SIMPLE>(a, hs, 0, v0, h.bits);
+        hist_add<SIMPLE>(a, hs, 1, v1, h.bits);
         if constexpr (NH == 2) {
-            if (pb_finite(o.v2)) hist_add<SIMPLE>(a, hs, 2, o.v2, h.bits);
-            if (a.method == PB_SHG && pb_finite(o.v3)) hist_add<SIMPLE>(a, hs, 3, o.v3, h.bits);
+            hist_add<SIMPLE>(a, hs, 2, o.v2, h.bits);
+            if (a.method == PB_SHG) hist_add<SIMPLE>(a, hs, 3, o.v3, h.bits);
         }
     }
     return o;
