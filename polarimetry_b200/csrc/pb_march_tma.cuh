@@ -74,9 +74,7 @@ __device__ __forceinline__ unsigned swz(int L, int half) { return (unsigned)(L *
 
 // NT: number of planes known at compile time (0 = run-time N): the harmonic sums are then fully unrolled and the basis constants
 // become immediate constant-bank operands (no loop control, no uniform loads)
-// FAST: whole-image thresholding (a.simple), the throughput-mode output set for every stack (a.all_lean), no PB_FLAG_PROJECT_ONLY, not the
-// redo pass -- established by the launcher, so that the per-pixel code carries none of those tests
-template <int NH, int BW, int MR, int NT, bool FAST = false>
+template <int NH, int BW, int MR, int NT>
 __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ CUtensorMap tmap, PixArgs a, typename BasisSel<NH>::type bs, TmaArgs ta) {
     constexpr int TR = MR + BW - 1;                     // tile rows
     constexpr int HH = BW / 2;                          // window extent before the centre (rows above / columns left)
@@ -84,7 +82,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     constexpr int FPD = FPB / 8;                        // filtered-tile row pitch in doubles
     constexpr int PLD = MR * FPD;                       // ... plane pitch in doubles
     extern __shared__ __align__(16) unsigned char smem[];
-    const bool redo = !FAST && ta.redo != nullptr;
+    const bool redo = ta.redo != nullptr;
     if (redo && !ta.redo[(size_t)blockIdx.y * gridDim.x + blockIdx.x]) return;
     const pb_outputs out = a.outs[blockIdx.y];
     const bool do_hist = !(a.flags & PB_FLAG_NO_HIST) && a.n_vars > 0 && out.hist;
@@ -215,10 +213,9 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     const bool pixw = warp < ta.pix_warps;
     const int pr = tid / XC, pj = tid - pr * XC;                   // pixel role
     const bool prow_ok = pixw && (y0 + pr) < H;
-    const int prow = (y0 + pr) * W;                               // H * W < 2^31 (pb_march_supported)
     const double *const pfp = fbuf + pr * FPD + pj;
-    const bool f64 = !FAST && (a.flags & PB_FLAG_OUT_F64);
-    const bool lean = FAST || store_is_lean<NH>(a, out);
+    const bool f64 = a.flags & PB_FLAG_OUT_F64;
+    const bool lean = store_is_lean<NH>(a, out);
     const unsigned sub2 = (unsigned)ta.isub * 0x10001u;
     const int ft = tid - ta.pix_warps * 32, nft = ta.t_warps * 32;   // T-warp thread index / count
 
@@ -295,10 +292,10 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
         if (pixw) {
             const int k = 16 * (u - 1) + pj - RX;
             if (prow_ok && k >= 0 && k < W) {
-                const long long p = (long long)(prow + k);
+                const long long p = (long long)(y0 + pr) * W + k;
                 const double I = pfp[N * PLD];                   // line N: the binned total intensity
                 bool cand;
-                if (FAST || a.simple) cand = I >= a.roi_ilow[0];
+                if (a.simple) cand = I >= a.roi_ilow[0];
                 else if (a.mask_in) cand = __ldg(a.mask_in + p) != 0;
                 else cand = roi_pass(a, a.roi_bits ? __ldg(a.roi_bits + p) : 1u, I);
                 if (redo && !cand) {
@@ -326,7 +323,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                             }
                             Sff = fma(f, f, Sff);                    // screening only
                         }
-                        const uint32_t bits = (FAST || a.simple || !a.roi_bits) ? 1u : __ldg(a.roi_bits + p);
+                        const uint32_t bits = (a.simple || !a.roi_bits) ? 1u : __ldg(a.roi_bits + p);
                         HarmPix hp = harm_stage_a_core<NH>(a, bits, S0, Sc, Ss, Sc4, Ss4, Sff);
                         if (hp.need) {
                             ExactAcc ex;
@@ -340,7 +337,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                         } else if (redo) {
                             emit = false;
                         }
-                        if (emit) o = harm_stage_b<NH, FAST ? 1 : 0>(a, hs, do_hist, hp);
+                        if (emit) o = harm_stage_b<NH>(a, hs, do_hist, hp);
                     }
                     if (emit) store_pixel<NH>(a, out, p, o, I, f64, lean);
                 }
@@ -403,12 +400,8 @@ size_t plan(const PixArgs &a, TmaArgs &ta) {
     return off;
 }
 
-template <int NH, int BW, int MR, int NT, bool FAST = false>
+template <int NH, int BW, int MR, int NT>
 cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int n_stacks, cudaStream_t st, const unsigned char *redo = nullptr) {
-    if constexpr (NH == 1 && NT == 18 && BW == 3 && MR == 16 && !FAST) {
-        // the headline configuration has a variant without the per-pixel generality tests
-        if (!redo && a.simple && a.all_lean && !(a.flags & PB_FLAG_PROJECT_ONLY)) return launch<NH, BW, MR, NT, true>(a, bs, n_stacks, st, nullptr);
-    }
     constexpr int TR = MR + BW - 1;
     TmaArgs ta;
     ta.redo = redo;
@@ -429,7 +422,7 @@ cudaError_t launch(const PixArgs &a, const typename BasisSel<NH>::type &bs, int 
     if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void *>(a.stack), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return cudaErrorInvalidValue;
-    auto kern = k_march_tma<NH, BW, MR, NT, FAST>;
+    auto kern = k_march_tma<NH, BW, MR, NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((a.H + MR - 1) / MR, n_stacks);
