@@ -138,54 +138,6 @@ __device__ __forceinline__ void lut_lookup(const PixArgs &a, double x, double y,
     rho = r; psi = q;
 }
 
-// The same lookup in two halves, for callers that keep several pixels in flight (pb_strip2.cuh): lut_issue starts every load of one
-// pixel's lookup (guessed cell; out-of-range or NaN coordinates are looked up at the grid centre and discarded), lut_finish verifies
-// the guess and interpolates. lut_finish(lut_issue(x, y)) == lut_lookup(x, y), operation for operation.
-struct LutReq {
-    double x, y, ga0, gb0, ga1, gb1;
-    double2 c0, c1, v00, v01, v10, v11;
-    int i0, i1;
-    bool in_range;
-};
-__device__ __forceinline__ LutReq lut_issue(const PixArgs &a, double x, double y) {
-    LutReq q;
-    q.in_range = x >= a.grid_lo && x <= a.grid_hi && y >= a.grid_lo && y <= a.grid_hi;      // false for NaN
-    q.x = q.in_range ? x : 0.0;
-    q.y = q.in_range ? y : 0.0;
-    const int n = a.lut_n;
-    q.i0 = max(0, min(__double2int_rd(fma(q.x, a.half_nm1, a.half_nm1)), n - 2));
-    q.i1 = max(0, min(__double2int_rd(fma(q.y, a.half_nm1, a.half_nm1)), n - 2));
-    q.ga0 = __ldg(a.grid + q.i0); q.gb0 = __ldg(a.grid + q.i0 + 1); q.ga1 = __ldg(a.grid + q.i1); q.gb1 = __ldg(a.grid + q.i1 + 1);
-    q.c0 = __ldg(a.lut_hy + q.i0); q.c1 = __ldg(a.lut_hy + q.i1);
-    const double2 *T = a.lut + (q.i0 * n + q.i1);
-    q.v00 = __ldg(T); q.v01 = __ldg(T + 1); q.v10 = __ldg(T + n); q.v11 = __ldg(T + n + 1);
-    return q;
-}
-__device__ __forceinline__ void lut_finish(const PixArgs &a, const LutReq &q, double &rho, double &psi) {
-    const int n = a.lut_n;
-    const double x = q.x, y = q.y;
-    double2 v00 = q.v00, v01 = q.v01, v10 = q.v10, v11 = q.v11;
-    double t0, t1;
-    if (x >= q.ga0 && (x < q.gb0 || q.i0 == n - 2) && y >= q.ga1 && (y < q.gb1 || q.i1 == n - 2)) {
-        const double d0 = x - q.ga0, q0 = d0 * q.c0.y, d1 = y - q.ga1, q1 = d1 * q.c1.y;
-        t0 = fma(fma(-q0, q.c0.x, d0), q.c0.y, q0);
-        t1 = fma(fma(-q1, q.c1.x, d1), q.c1.y, q1);
-    } else {
-        const int i0 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, x, t0);
-        const int i1 = lut_axis(a.grid, a.lut_hy, n, a.half_nm1, y, t1);
-        const double2 *T = a.lut + (i0 * n + i1);
-        v00 = __ldg(T); v01 = __ldg(T + 1); v10 = __ldg(T + n); v11 = __ldg(T + n + 1);
-    }
-    const double u0 = 1.0 - t0, u1 = 1.0 - t1;
-    const double w00 = u0 * u1, w01 = u0 * t1, w10 = t0 * u1, w11 = t0 * t1;
-    double r = v00.x * w00, p = v00.y * w00;
-    r = r + v01.x * w01; p = p + v01.y * w01;
-    r = r + v10.x * w10; p = p + v10.y * w10;
-    r = r + v11.x * w11; p = p + v11.y * w11;
-    rho = q.in_range ? r : pb_nan();
-    psi = q.in_range ? p : pb_nan();
-}
-
 constexpr double PB_RAD2DEG = 180.0 / 3.141592653589793238462643383279502884;
 constexpr double PB_DEG2RAD = 3.141592653589793238462643383279502884 / 180.0;
 

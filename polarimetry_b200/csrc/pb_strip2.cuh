@@ -233,8 +233,8 @@ __global__ void __maxnreg__(PB_STRIP2_MAXREG) k_strip2(const __grid_constant__ C
             const double2 e0 = fin[0], e1 = fin[32], e2 = fin[64], e3 = fin[96], eI = fin_I[0];
             if constexpr (FAST) {
                 // whole-image thresholding, float32 maps + mask (established by the launcher). (Measured: running the lane's two pixels
-                // side by side on stand-in values for the ones that take no part -- lut_issue / lut_finish -- costs more instructions
-                // than the overlap of their latencies buys: 361 k -> 321 k Mpx-angles/s.)
+                // side by side on stand-in values for the ones that take no part costs more instructions than the overlap of their
+                // latencies buys: 361 k -> 321 k Mpx-angles/s.)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int k = k0 + c;
