@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 TAG = os.environ.get('PB_BUILD_TAG', '')          # developer A/B builds: libpolarb200_<tag>.so (select with PB_LIB=...)
 LIB = PKG / (f'libpolarb200_{TAG}.so' if TAG else 'libpolarb200.so')
-SOURCES = ['pb_strip_1.cu', 'pb_march_tma_1.cu', 'pb_march_tma_2.cu', 'pb_march_u16_1.cu', 'pb_march_u16_2.cu', 'pb_pixel.cu', 'pb_march_u8_1.cu', 'pb_march_u8_2.cu', 'pb_api.cu', 'pb_box.cu', 'pb_march.cu',
+SOURCES = ['pb_strip_1.cu', 'pb_march_tma_1.cu', 'pb_march_tma_2.cu', 'pb_march_tma_4p.cu', 'pb_march_u16_1.cu', 'pb_march_u16_2.cu', 'pb_pixel.cu', 'pb_march_u8_1.cu', 'pb_march_u8_2.cu', 'pb_api.cu', 'pb_box.cu', 'pb_march.cu',
            'pb_reduce.cu', 'pb_compact.cu', 'pb_ingest.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -555,8 +555,14 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
         a.stack = stacks; a.stack_stride = (long long)p->N * P; a.outs = od;
         unsigned char *redo = redo_slot(ctx, (size_t)n_stacks * ((p->H + 15) / 16));
         if (!redo) return fail(ctx, PB_ERR_NOMEM, "pb_analyze: cudaMalloc of the redo flags failed");
-        CK(pb_launch_march(a, ctx->basis, p, n_stacks, st, &ctx->launches, redo));
-        return PB_OK;
+        const cudaError_t me = pb_launch_march(a, ctx->basis, p, n_stacks, st, &ctx->launches, redo);
+        if (me == cudaSuccess) return PB_OK;
+        // 4POLAR has no register-staged march: a stack the tensor map cannot describe (address / width) takes the unfused kernels
+        if (!(p->method >= PB_4POLAR_2D && (me == cudaErrorInvalidConfiguration || me == cudaErrorNotSupported))) {
+            ctx->err = std::string("pb_launch_march: ") + cudaGetErrorString(me);
+            return PB_ERR_CUDA;
+        }
+        a.stack = nullptr;
     }
     // unfused: intensity -> box ; field -> box(H) -> box(W) ; per-pixel kernel on the double field
     const size_t fbytes = sizeof(double) * (size_t)p->N * P;

@@ -8,6 +8,7 @@ cudaError_t pb_march_u8_nh1(const PixArgs &a, const Basis1 &bs, const pb_params 
 cudaError_t pb_march_u8_nh2(const PixArgs &a, const Basis2 &bs, const pb_params *p, int n_stacks, cudaStream_t st);
 cudaError_t pb_march_tma_nh1(const PixArgs &a, const Basis1 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_1.cu
 cudaError_t pb_march_tma_nh2(const PixArgs &a, const Basis2 &bs, int bw, int n_stacks, cudaStream_t st);   // pb_march_tma_2.cu
+cudaError_t pb_march_tma_4polar(const PixArgs &a, int bw, int n_stacks, cudaStream_t st);                     // pb_march_tma_4p.cu
 cudaError_t pb_strip_nh1(const PixArgs &a, const Basis1 &bs, int bw, int n_stacks, unsigned char *redo, cudaStream_t st);   // pb_strip_1.cu
 cudaError_t pb_march_tma_redo_nh1_bw3_n18(const PixArgs &a, const Basis1 &bs, int n_stacks, const unsigned char *redo, cudaStream_t st);
 
@@ -34,7 +35,14 @@ static bool strip_eligible(const PixArgs &a, const pb_params *p, const unsigned 
 // dark / dark+removed (so that the H pass sums integers), bin_w <= 8, N + 1 <= 32 chain warps. Everything else
 // (CARS, 4POLAR, float stacks, fractional dark, wider windows, more angles) takes the unfused kernels.
 bool pb_march_supported(const pb_params *p) {
-    if (p->method == PB_CARS || p->method >= PB_4POLAR_2D) return false;
+    if (p->method == PB_CARS) return false;
+    if (p->method >= PB_4POLAR_2D) {
+        // 4POLAR with binning: the TMA kernel only (uint16 stack of 4 planes, square window 2..8, integer dark); pb_analyze falls back to
+        // the unfused kernels when the stack's address / width do not satisfy the tensor-map rules
+        const double sub = p->dark + p->removed_intensity;
+        return p->dtype == PB_U16 && p->N == 4 && p->bin_h == p->bin_w && p->bin_w >= 2 && p->bin_w <= 8 && sub == floor(sub) && p->dark == floor(p->dark) &&
+               sub >= 0 && sub <= 65535.0 && p->dark >= 0 && p->dark <= 65535.0 && (long long)p->H * p->W < 2147483647LL;
+    }
     if (p->dtype != PB_U8 && p->dtype != PB_U16) return false;
     const double sub = p->dark + p->removed_intensity;
     if (sub != floor(sub) || p->dark != floor(p->dark) || sub < 0 || sub > 65535.0 || p->dark < 0 || p->dark > 65535.0) return false;
@@ -61,6 +69,12 @@ cudaError_t pb_launch_march(const PixArgs &a, const Basis2 &bs, const pb_params 
                             unsigned char *redo) {
     cudaError_t e;
     const bool tma_ok = tma_eligible(a, p);
+    if (p->method >= PB_4POLAR_2D) {
+        if (!tma_ok) return cudaErrorInvalidConfiguration;
+        e = pb_march_tma_4polar(a, p->bin_w, n_stacks, st);
+        if (e == cudaSuccess && launches) ++*launches;
+        return e;
+    }
     if (p->method == PB_1PF) {
         Basis1 b1;
         memcpy(b1.c2, bs.c2, sizeof(b1.c2)); memcpy(b1.s2, bs.s2, sizeof(b1.s2));

@@ -21,7 +21,7 @@
 #pragma once
 #include <cuda.h>
 #include <cstdlib>
-#include "pb_pixel.cuh"
+#include "pb_pixel4.cuh"
 
 void pb_ddrecip(int n, double *hi, double *lo);   // pb_api.cu
 
@@ -215,7 +215,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
     const bool prow_ok = pixw && (y0 + pr) < H;
     const double *const pfp = fbuf + pr * FPD + pj;
     const bool f64 = a.flags & PB_FLAG_OUT_F64;
-    const bool lean = store_is_lean<NH>(a, out);
+    const bool lean = NH != 0 && store_is_lean<(NH ? NH : 1)>(a, out);
     const unsigned sub2 = (unsigned)ta.isub * 0x10001u;
     const int ft = tid - ta.pix_warps * 32, nft = ta.t_warps * 32;   // T-warp thread index / count
 
@@ -294,6 +294,11 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
             if (prow_ok && k >= 0 && k < W) {
                 const long long p = (long long)(y0 + pr) * W + k;
                 const double I = pfp[N * PLD];                   // line N: the binned total intensity
+                if constexpr (NH == 0) {
+                    // 4POLAR (N = 4): the binned planes in the order of PP:2957 (acquisition planes 1 and 2 swapped) -> PP:3001-3014, 3041-3051
+                    const double f4[4] = {pfp[0], pfp[2 * PLD], pfp[PLD], pfp[3 * PLD]};
+                    p4_pixel<false>(a, hs, do_hist, out, p, f4, I);
+                } else {
                 bool cand;
                 if (a.simple) cand = I >= a.roi_ilow[0];
                 else if (a.mask_in) cand = __ldg(a.mask_in + p) != 0;
@@ -340,6 +345,7 @@ __global__ void __maxnreg__(PB_TMA_MAXREG) k_march_tma(const __grid_constant__ C
                         if (emit) o = harm_stage_b<NH>(a, hs, do_hist, hp);
                     }
                     if (emit) store_pixel<NH>(a, out, p, o, I, f64, lean);
+                }
                 }
             }
         } else if (u + 1 <= U) {

@@ -542,3 +542,28 @@ def test_histogram_match_aggregation_on_an_aligned_sample(eng):
         assert hr[:3].sum() > 0.9 * hr.sum()                     # an aligned sample: three bins hold nearly every pixel
         for va, vb in zip(a.vars, b.vars):
             assert util.eq(va.values.cpu().numpy(), vb.values.cpu().numpy())
+
+
+def test_4polar_binned_takes_the_fused_march(eng):
+    """4POLAR with spatial binning runs in ONE launch of the row-march kernel (box filter of the four channel planes + the
+    polarization-matrix inversion of PP:3001-3014 / 3041-3051 per pixel); a stack whose width the tensor map cannot describe falls
+    back to the unfused kernels with the same results."""
+    from polarimetry_b200 import synth
+    for name in ('4polar3d_bin3', '4polar2d_bin3'):
+        c = util.CASE_BY_NAME[name]
+        g = util.golden(name)
+        n0 = eng.launch_count()
+        res = eng.analyze(g['values'], params_for(c), calib_for(c), c['rois'], c['per_roi'])
+        assert res.plan == 'fused_march' and eng.launch_count() - n0 == 1
+        check_against_golden(c, res, g, exact_maps=True)
+    cal = calib_for(util.CASE_BY_NAME['4polar3d_bin3'])
+    for shape in ((40, 52), (64, 96), (17, 16)):
+        v = synth.stack_4polar(*shape, seed=3, three_d=True)
+        kw = dict(method='4POLAR 3D', dark=0.0, bins=(3, 3), ilow=1000.0)
+        a = eng.analyze(v, AnalysisParams(**kw), cal)
+        b = eng.analyze(v, AnalysisParams(force_unfused=True, **kw), cal)
+        for va, vb in zip(a.vars, b.vars):
+            assert torch.equal(torch.nan_to_num(va.values, nan=-1.0), torch.nan_to_num(vb.values, nan=-1.0)), (shape, va.name)
+        assert torch.equal(a.mask, b.mask) and torch.equal(a.intensity, b.intensity)
+        for k in a.hist:
+            assert util.eq(a.hist[k], b.hist[k]), (shape, k)
