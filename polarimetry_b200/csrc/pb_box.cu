@@ -9,6 +9,9 @@
 // the parallelism is over lines: one thread per column for the H pass, one thread per row for the W pass,
 // the latter staged through shared memory so that global traffic stays coalesced.
 #include "pb_dev.cuh"
+#include <cstdlib>
+
+void pb_ddrecip(int n, double *hi, double *lo);   // pb_api.cu
 
 namespace {
 
@@ -32,8 +35,17 @@ __global__ void k_isum(const T *__restrict__ v, double *__restrict__ out, long l
     }
 }
 
-// H pass: thread = (plane, x); walks y. Coalesced across x. Out of place.
-__global__ void k_box_y(const double *__restrict__ in, double *__restrict__ out, int planes, int H, int W, int n) {
+// tmp / n, correctly rounded without a division: fma(x, rhi, x*rlo) with (rhi, rlo) the double-double 1/n (tests/test_shortcuts.py:
+// x/n is never within 2^-60 of a rounding boundary, the approximation error is 2^-105); values outside the range where neither
+// product can underflow or overflow (never produced by image data) take the IEEE division
+__device__ __forceinline__ double div_small(double x, double rhi, double rlo, double dn) {
+    const double ax = fabs(x);
+    return ((ax > 1e-280 && ax < 1e280) || x == 0.0) ? fma(x, rhi, x * rlo) : x / dn;
+}
+
+// H pass: thread = (plane, x); walks y, four rows at a time so that their eight loads are in flight together. Coalesced across x.
+// Out of place.
+__global__ void k_box_y(const double *__restrict__ in, double *__restrict__ out, int planes, int H, int W, int n, double rhi, double rlo) {
     const long long cols = (long long)planes * W;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
@@ -45,12 +57,26 @@ __global__ void k_box_y(const double *__restrict__ in, double *__restrict__ out,
     const double dn = (double)n;
     double tmp = 0.0;
     for (int k = 0; k < n; ++k) tmp = tmp + src[(long long)pb_reflect(k - h, H) * W];
-    dst[0] = tmp / dn;
-    for (int k = 1; k < H; ++k) {
+    dst[0] = div_small(tmp, rhi, rlo, dn);
+    int k = 1;
+    for (; k + 3 < H; k += 4) {
+        double nw[4], od[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nw[j] = src[(long long)pb_reflect(k + j + n - 1 - h, H) * W];
+            od[j] = src[(long long)pb_reflect(k + j - 1 - h, H) * W];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tmp = tmp + (nw[j] - od[j]);
+            dst[(long long)(k + j) * W] = div_small(tmp, rhi, rlo, dn);
+        }
+    }
+    for (; k < H; ++k) {
         double nw = src[(long long)pb_reflect(k + n - 1 - h, H) * W];
         double od = src[(long long)pb_reflect(k - 1 - h, H) * W];
         tmp = tmp + (nw - od);
-        dst[(long long)k * W] = tmp / dn;
+        dst[(long long)k * W] = div_small(tmp, rhi, rlo, dn);
     }
 }
 
@@ -60,7 +86,7 @@ constexpr int BX_ROWS = 64;   // rows per block = threads per block
 constexpr int BX_RING = 64;   // ring entries per row (n <= 32)
 constexpr int BX_LD = BX_RING + 1;
 
-__global__ void __launch_bounds__(BX_ROWS) k_box_x(const double *__restrict__ in, double *__restrict__ out, long long rows, int W, int n) {
+__global__ void __launch_bounds__(BX_ROWS) k_box_x(const double *__restrict__ in, double *__restrict__ out, long long rows, int W, int n, double rhi, double rlo) {
     extern __shared__ __align__(16) unsigned char bx_smem[];
     double *ring = reinterpret_cast<double *>(bx_smem);   // [BX_ROWS][BX_LD]
     double *obuf = ring + BX_ROWS * BX_LD;                 // [BX_ROWS][33]
@@ -93,7 +119,7 @@ __global__ void __launch_bounds__(BX_ROWS) k_box_x(const double *__restrict__ in
                 } else {
                     tmp = tmp + (rg[(j + n - 1) & (BX_RING - 1)] - rg[(j - 1) & (BX_RING - 1)]);
                 }
-                ob[j - jbeg] = tmp / dn;
+                ob[j - jbeg] = div_small(tmp, rhi, rlo, dn);
             }
         }
         __syncthreads();
@@ -106,6 +132,43 @@ __global__ void __launch_bounds__(BX_ROWS) k_box_x(const double *__restrict__ in
         // the next tile overwrites ring slots of tile m-1 and obuf: all reads above are done after this barrier
         __syncthreads();
     }
+}
+
+// W pass, one thread per row reading and writing its row directly (no shared-memory staging, no block barriers): consecutive steps of a
+// thread touch consecutive doubles, so every 32-byte sector it fetches or writes is used in full (4 steps); the entering and the
+// leaving element of the window are loaded four steps at a time. Same operations in the same order as k_box_x.
+__global__ void k_box_x_rows(const double *__restrict__ in, double *__restrict__ out, long long rows, int W, int n, double rhi, double rlo) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double *src = in + r * W;
+    double *dst = out + r * W;
+    const int h = n / 2;
+    const double dn = (double)n;
+    double tmp = 0.0;
+    for (int k = 0; k < n; ++k) tmp = tmp + src[pb_reflect(k - h, W)];
+    dst[0] = div_small(tmp, rhi, rlo, dn);
+    // output j: entering element ext[j+n-1] = src[reflect(j+n-1-h)], leaving element ext[j-1] = src[reflect(j-1-h)]
+    auto step = [&](int j) {
+        const double nw = src[pb_reflect(j + n - 1 - h, W)], od = src[pb_reflect(j - 1 - h, W)];
+        tmp = tmp + (nw - od);
+        dst[j] = div_small(tmp, rhi, rlo, dn);
+    };
+    int j = 1;
+    const int j_in = min(h + 1, W);                 // first output whose two elements lie inside the row without reflection
+    for (; j < j_in; ++j) step(j);
+    const int j_last = W - n + h;                   // last such output
+    for (; j + 3 <= j_last; j += 4) {
+        double nw[4], od[4];
+        const double *pn = src + (j + n - 1 - h), *po = src + (j - 1 - h);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { nw[q] = pn[q]; od[q] = po[q]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            tmp = tmp + (nw[q] - od[q]);
+            dst[j + q] = div_small(tmp, rhi, rlo, dn);
+        }
+    }
+    for (; j < W; ++j) step(j);
 }
 
 }  // namespace
@@ -143,16 +206,28 @@ cudaError_t pb_launch_isum(const void *v, int dtype, double *out, long long P, i
 cudaError_t pb_launch_box_y(const double *in, double *out, int planes, int H, int W, int n, cudaStream_t st) {
     const int threads = 128;
     long long cols = (long long)planes * W;
-    k_box_y<<<(unsigned)((cols + threads - 1) / threads), threads, 0, st>>>(in, out, planes, H, W, n);
+    double rhi, rlo;
+    pb_ddrecip(n, &rhi, &rlo);
+    k_box_y<<<(unsigned)((cols + threads - 1) / threads), threads, 0, st>>>(in, out, planes, H, W, n, rhi, rlo);
     return cudaGetLastError();
 }
 
 // in -> out along W (1 < n <= 32)
 cudaError_t pb_launch_box_x(const double *in, double *out, int planes, int H, int W, int n, cudaStream_t st) {
     long long rows = (long long)planes * H;
+    static const bool staged = [] { const char *e = getenv("PB_BOX_X_STAGED"); return e && atoi(e) != 0; }();   // A/B: the shared-memory staged kernel
+    if (!staged) {
+        double rhi, rlo;
+        pb_ddrecip(n, &rhi, &rlo);
+        const int threads = rows >= 148LL * 256 ? 128 : 32;        // few rows (one plane): spread them over the SMs
+        k_box_x_rows<<<(unsigned)((rows + threads - 1) / threads), threads, 0, st>>>(in, out, rows, W, n, rhi, rlo);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(double) * BX_ROWS * (BX_LD + 33);
     cudaError_t e = cudaFuncSetAttribute(k_box_x, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_box_x<<<(unsigned)((rows + BX_ROWS - 1) / BX_ROWS), BX_ROWS, smem, st>>>(in, out, rows, W, n);
+    double rhi, rlo;
+    pb_ddrecip(n, &rhi, &rlo);
+    k_box_x<<<(unsigned)((rows + BX_ROWS - 1) / BX_ROWS), BX_ROWS, smem, st>>>(in, out, rows, W, n, rhi, rlo);
     return cudaGetLastError();
 }
