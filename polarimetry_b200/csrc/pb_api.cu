@@ -564,21 +564,20 @@ int pb_analyze(pb_ctx *ctx, const pb_params *p, const void *stacks, int n_stacks
         }
         a.stack = nullptr;
     }
-    // unfused: intensity -> box ; field -> box(H) -> box(W) ; per-pixel kernel on the double field
-    const size_t fbytes = sizeof(double) * (size_t)p->N * P;
+    // unfused: field planes + the total-intensity image as one more plane -> box(H) -> box(W) (one launch each over the N + 1 planes);
+    // per-pixel kernel on the double field
+    const size_t fbytes = sizeof(double) * (size_t)(p->N + 1) * P;
     if ((rc = ws_reserve(ctx, 0, fbytes))) return rc;
     if ((rc = ws_reserve(ctx, 1, fbytes))) return rc;
-    if ((rc = ws_reserve(ctx, 2, sizeof(double) * P))) return rc;
-    if ((rc = ws_reserve(ctx, 3, sizeof(double) * P))) return rc;
     const size_t esz = dtype_size(p->dtype);
     if ((rc = ws_acquire(ctx, st))) return rc;
     for (int s = 0; s < n_stacks; ++s) {
         const char *src = (const char *)stacks + (size_t)s * p->N * P * esz;
-        double *Ires, *Fres;
-        CK(pb_launch_isum(src, p->dtype, (double *)ctx->ws[2], P, p->N, p->dark, st)); ctx->launches++;
-        if ((rc = run_box(ctx, (double *)ctx->ws[2], (double *)ctx->ws[3], 1, p->H, p->W, p->bin_h, p->bin_w, st, &Ires))) return rc;
+        double *Fres;
+        CK(pb_launch_isum(src, p->dtype, (double *)ctx->ws[0] + (size_t)p->N * P, P, p->N, p->dark, st)); ctx->launches++;
         CK(pb_launch_field(src, p->dtype, (double *)ctx->ws[0], P, p->N, a.sub, a.do_sqrt, p->method >= PB_4POLAR_2D, st)); ctx->launches++;
-        if ((rc = run_box(ctx, (double *)ctx->ws[0], (double *)ctx->ws[1], p->N, p->H, p->W, p->bin_h, p->bin_w, st, &Fres))) return rc;
+        if ((rc = run_box(ctx, (double *)ctx->ws[0], (double *)ctx->ws[1], p->N + 1, p->H, p->W, p->bin_h, p->bin_w, st, &Fres))) return rc;
+        const double *Ires = Fres + (size_t)p->N * P;
         PixArgs b = a;
         b.stack = Fres; b.stack_stride = 0; b.from_field = 1; b.do_sqrt = 0; b.intensity_in = Ires; b.outs = od + s;
         if ((rc = launch_pixel(ctx, p, b, PB_F64, 1, st))) return rc;
